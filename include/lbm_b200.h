@@ -1,0 +1,131 @@
+/*
+ * lbm_b200.h -- C ABI of the B200-native D2Q9 lid-driven-cavity collide-and-stream step.
+ *
+ * This is the drop-in boundary for ONE hot path of RaghuvirJonnagiri/LatticeBoltzmannSimulations:
+ * the per-time-step update "moments -> collision (SRT/TRT/MRT) -> streaming -> wall + moving-lid rule".
+ * Every entry point names the reference interface it replaces (file:line into the upstream repo).
+ * Plain C: opaque handle, plain pointers and sizes, int return codes (0 = ok) plus a thread-local
+ * error string.  No torch / numpy types appear here; Python binds it with ctypes
+ * (latticeboltzmannsimulations_b200/_capi.py), and INTEGRATION.md shows the reference-side stubs.
+ *
+ * Host array convention = the reference's: populations [9][nx][ny] (y fastest), rho [nx][ny],
+ * u [2][nx][ny]; y == 0 is the moving lid, y == ny-1 the bottom wall (MRT.py:252-261).  The device
+ * layout (SoA, x fastest, one ghost row above and below each y-strip) is private to the library and
+ * described by lbm_get_layout() for callers that exchange halo rows themselves.
+ *
+ * Semantics: "C" of SURVEY.md 3.4 == MRT_GPU.py funRT + funBC (push + non-equilibrium bounce-back),
+ * re-expressed as one fused pull pass (oracle/lbm_oracle.py step_C_pull is the executable spec).
+ * There is NO CPU fallback: every call fails with LBM_ECUDA when no CUDA device is usable.
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_B200_ABI_VERSION 1
+
+enum lbm_status { LBM_OK = 0, LBM_EINVAL = 1, LBM_ECUDA = 2, LBM_ENOMEM = 3, LBM_ESTATE = 4 };
+enum lbm_dtype { LBM_F32 = 0, LBM_F64 = 1 };
+/* `RT` of MRT_GPU.py:48 */
+enum lbm_collision { LBM_SRT = 0, LBM_TRT = 1, LBM_MRT = 2 };
+/* which rows of the local strip a launch covers (multi-GPU overlap of halo exchange and interior) */
+enum lbm_region { LBM_REGION_ALL = 0, LBM_REGION_EDGE = 1, LBM_REGION_INTERIOR = 2 };
+/* kernel family: plain coalesced loads, or TMA-staged persistent tiles */
+enum lbm_engine { LBM_ENGINE_AUTO = 0, LBM_ENGINE_LDG = 1, LBM_ENGINE_TMA = 2 };
+
+typedef struct lbm_solver* lbm_handle_t;
+
+/* Replaces the module-level constants at the top of every solver script
+ * (MRT_GPU.py:45-58: RT, turb, xsize, ysize; MRT_GPU_datagen.py:55-70 for the batch of cavities). */
+typedef struct lbm_config {
+    int32_t nx, ny;       /* global cavity size in nodes (no multiple-of-32 restriction, cf. MRT_GPU.py:53-54) */
+    int32_t batch;        /* independent cavities held by this handle (MRT_GPU_datagen.py Re sweep) */
+    int32_t dtype;        /* lbm_dtype: storage and arithmetic type */
+    int32_t collision;    /* lbm_collision */
+    int32_t turb;         /* 1 = Smagorinsky closure of MRT_GPU.py:570-589 */
+    int32_t y0;           /* first global row owned by this handle (y-strip decomposition) */
+    int32_t ny_local;     /* rows owned; 0 means the whole cavity (y0 must then be 0) */
+    int32_t device;       /* CUDA device ordinal, -1 = current device */
+    int32_t engine;       /* lbm_engine */
+    void* ext_f[2];       /* optional caller-owned device buffers (e.g. torch tensors) for the A/B population
+                             arrays, each lbm_state_bytes() long; NULL = the library allocates */
+} lbm_config_t;
+
+/* Private device layout, for callers that move halo rows themselves (NCCL send/recv on row views). */
+typedef struct lbm_layout {
+    int64_t elem_size;      /* 4 or 8 */
+    int64_t pitch;          /* elements per stored row (>= nx, multiple of 32) */
+    int64_t rows;           /* stored rows per population plane = ny_local + 2 (ghost row first and last) */
+    int64_t plane;          /* elements per population plane = rows * pitch */
+    int64_t cavity;         /* elements per cavity = 9 * plane */
+    int64_t state_bytes;    /* bytes of one A/B buffer = batch * cavity * elem_size */
+} lbm_layout_t;
+
+const char* lbm_last_error(void);
+int lbm_abi_version(void);
+int lbm_device_count(int* count);
+
+/* Size of one population buffer for this configuration (so the caller can allocate ext_f). */
+int lbm_state_bytes(const lbm_config_t* cfg, size_t* bytes);
+
+/* cuda.mem_alloc x8 + constants of MRT_GPU.py:309-328 -> one handle. */
+int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out);
+int lbm_destroy(lbm_handle_t h);
+int lbm_get_layout(lbm_handle_t h, lbm_layout_t* out);
+
+/* functions.pyx:38-43 set_omega(uLB, Re, ysize) / MRT_GPU.py:63-65: omega = 2 / (6 uLB ny / Re + 1); the other
+ * MRT rates take the GPU-script values (omega_e 1.0, omega_eps = omega_q = 1.2, MRT_GPU.py:88-91) and the TRT
+ * omega- follows MRT_GPU.py:82-84.  cavity = -1 applies to every cavity of the batch. */
+int lbm_set_reynolds(lbm_handle_t h, int cavity, double uLB, double Re);
+/* Explicit rates (the literals spliced into the kernel source at MRT_GPU.py:422,531,662). */
+int lbm_set_rates(lbm_handle_t h, int cavity, double uLB, double omega_nu, double omega_e,
+                  double omega_eps, double omega_q, double omega_minus);
+
+/* Host init of MRT_GPU.py:259-267 + uploads :323-328: rho = 1, u = (uLB,0) on row y = 0, f = feq. */
+int lbm_init_equilibrium(lbm_handle_t h);
+/* cuda.memcpy_htod(fin_g, fin) (MRT_GPU.py:323) incl. the [k,x,y]->[k,y,x] transposes of :283-289.
+ * f: [batch][9][nx][ny_local] in the handle's dtype; on_device != 0 means `f` is a device pointer. */
+int lbm_upload_f(lbm_handle_t h, const void* f, int on_device, void* stream);
+/* cuda.memcpy_dtoh(fin, ftemp_g) + transposes (MRT_GPU.py:755, 758-760): the reference's `fin` after the
+ * steps taken so far.  Does not disturb the state. */
+int lbm_download_f(lbm_handle_t h, void* f, int on_device, void* stream);
+
+/* The hot call.  Replaces the Python time loop body of MRT_GPU.py:707-732 (funRT + funBC launches) and the
+ * per-step functions.allfunc of MRT_cython.py:453.  Runs `nsteps` fused steps asynchronously on `stream`
+ * (a cudaStream_t, NULL = default stream).  With write_macros != 0 the LAST step also stores rho and u as the
+ * reference does every step: the overridden moments of the state that entered that step. */
+int lbm_step(lbm_handle_t h, int nsteps, int write_macros, void* stream);
+
+/* One step restricted to a row region, without advancing the step counter; lbm_swap() completes the step.
+ * Used by the y-strip driver: EDGE rows first, halo rows exchanged while INTERIOR runs. */
+int lbm_step_region(lbm_handle_t h, int region, int write_macros, void* stream);
+int lbm_swap(lbm_handle_t h);
+/* Device pointers of the buffer being read (which = 0) / written (which = 1) by the next lbm_step_region. */
+int lbm_buffer_ptr(lbm_handle_t h, int which, void** ptr);
+
+/* cuda.memcpy_dtoh(rho, rho_g) / (u, u_g) + transposes (MRT_GPU.py:756-760): rho [batch][nx][ny_local],
+ * u [batch][2][nx][ny_local].  Either pointer may be NULL. */
+int lbm_get_macros(lbm_handle_t h, void* rho, void* u, int on_device, void* stream);
+/* Same fields evaluated from the CURRENT populations (no one-step lag). */
+int lbm_get_macros_current(lbm_handle_t h, void* rho, void* u, int on_device, void* stream);
+
+/* functions.equ(rho, ux, uy) (functions.pyx:229-267, == MRT.py:213-231): second-order equilibrium of arbitrary
+ * fields, stateless.  rho, ux, uy: [n] values; feq: [9][n]; dtype = lbm_dtype; on_device != 0 for device pointers. */
+int lbm_equilibrium(int dtype, int64_t n, const void* rho, const void* ux, const void* uy, void* feq,
+                    int on_device, void* stream);
+
+int lbm_sync(lbm_handle_t h);
+/* Steps completed, and number of kernels this handle has launched (for the bench's gpu_launches). */
+int lbm_get_counters(lbm_handle_t h, int64_t* steps_done, int64_t* kernel_launches);
+/* Name of the kernel family in use ("ldg" / "tma"). */
+const char* lbm_engine_name(lbm_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

@@ -1,0 +1,69 @@
+"""Script-level entry points of the reference, as callables.
+
+The upstream solvers are flat scripts: edit ``Re``, ``xsize, ysize``, ``uLB``, ``maxIt``, ``RT`` at the top
+(``MRT_GPU.py:45-58``), run, and read ``rho[x,y]``, ``u[2,x,y]``, ``fin[9,x,y]`` from the globals
+(``:752-760``); ``MRT_GPU_datagen.py`` wraps the same loop in ``for Re in Re_range`` (``:55-57``) and stacks
+``f_final[N,9,nx,ny]``, ``u_final[N,2,nx,ny]`` (``:879-902``).  These functions expose exactly those inputs and
+outputs; the time loop runs on the GPU through the C ABI.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .solver import CavitySolver
+
+
+def run_cavity(nx: int, ny: int, Re: float, uLB: float = 0.08, steps: int = 1000, collision: str = "MRT",
+               dtype="float64", turb: bool = False, f0=None, return_f: bool = False, current_macros: bool = False,
+               device: Optional[int] = None, engine: str = "auto"):
+    """One lid-driven cavity: returns ``(rho[nx,ny], u[2,nx,ny])`` (+ ``f[9,nx,ny]`` with ``return_f``).
+
+    ``rho, u`` carry the reference's one-step lag (they are the moments of the state that entered the last step);
+    pass ``current_macros=True`` for the moments of the returned ``f`` instead.  ``f0`` (``[9,nx,ny]``, host array,
+    e.g. pinned) replaces the equilibrium start ``rho = 1, u = (uLB,0)`` on the lid row (``MRT_GPU.py:259-267``).
+    """
+    with CavitySolver(nx, ny, 1, dtype, collision, turb, device=device, engine=engine) as s:
+        s.set_reynolds(Re, uLB)
+        if f0 is None:
+            s.init_equilibrium()
+        else:
+            s.upload_f(f0)
+        s.step(int(steps), write_macros=True)
+        rho, u = s.macros(current=current_macros)
+        if return_f:
+            return rho, u, s.download_f()
+        return rho, u
+
+
+def datagen(Re_list: Sequence[float], nx: int = 384, ny: int = 384, uLB: float = 0.08, steps: int = 10000,
+            collision: str = "MRT", dtype="float32", device: Optional[int] = None, engine: str = "auto",
+            chunk: Optional[int] = None):
+    """Batched Reynolds sweep of ``MRT_GPU_datagen.py``: every cavity of ``Re_list`` advanced ``steps`` steps.
+
+    Returns ``(f_final[N,9,nx,ny], u_final[N,2,nx,ny], feq_initial[9,nx,ny], Re_range[N])`` in the dtype / ``[x,y]``
+    indexing of the files the reference saves (``:899-902``).  Cavities are independent (no communication); the
+    multi-GPU driver (``distributed.datagen_sharded``) gives rank r the cavities ``r::world``.
+    """
+    Re_arr = np.asarray(list(Re_list), dtype=np.float64)
+    n = len(Re_arr)
+    _, npdt = {"float32": (0, np.float32), "float64": (1, np.float64)}[np.dtype(dtype).name]
+    f_final = np.empty((n, 9, nx, ny), dtype=npdt)
+    u_final = np.empty((n, 2, nx, ny), dtype=npdt)
+    feq_initial = None
+    chunk = n if chunk is None else max(1, int(chunk))
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        with CavitySolver(nx, ny, hi - lo, dtype, collision, device=device, engine=engine) as s:
+            s.set_reynolds(Re_arr[lo:hi], uLB)
+            s.init_equilibrium()
+            if feq_initial is None:
+                f_init = s.download_f()
+                feq_initial = np.array(f_init if hi - lo == 1 else f_init[0])
+            s.step(int(steps), write_macros=True)
+            _, u = s.macros()
+            f = s.download_f()
+            f_final[lo:hi] = f.reshape(hi - lo, 9, nx, ny)
+            u_final[lo:hi] = u.reshape(hi - lo, 2, nx, ny)
+    return f_final, u_final, feq_initial, Re_arr

@@ -1,0 +1,758 @@
+// C-ABI implementation (include/lbm_b200.h) and the "ldg" kernel family of the fused D2Q9 step.
+//
+// Device layout (private; lbm_get_layout): population buffers A and B, each
+//     [cavity b][population k][stored row r = 0 .. ny_local+1][pitch]      x fastest,
+// stored row r holds local row r-1; rows 0 and ny_local+1 are ghost rows (neighbour strip's edge rows, filled by the
+// halo exchange; never read where they fall outside the physical cavity).  Between steps a buffer holds the
+// POST-collision populations; the next launch pulls them (streaming), applies the wall rule, collides and stores
+// into the other buffer.  Side buffers carry what the wall rule needs from the previous step: rho_lid[b][x] and the
+// four doubly-orphaned corner populations carry[b][4] (see oracle/lbm_oracle.py PullState).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lbm_b200.h"
+#include "lbm_device.cuh"
+
+using namespace lbm;
+
+// ------------------------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(e__ == cudaErrorMemoryAllocation ? LBM_ENOMEM : LBM_ECUDA,                       \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                            \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// kernel arguments
+// ------------------------------------------------------------------------------------------------------------
+struct StepArgs {
+    const void* src;
+    void* dst;
+    void* rho;
+    void* ux;
+    void* uy;
+    void* rho_lid;             // [batch][pitch]
+    void* carry;               // [batch][4]
+    const CavityParams* cav;   // [batch]
+    int nx, ny, y0, nyl, pitch;
+    long long plane, cavity;   // elements
+    long long mplane;          // macro plane = nyl * pitch elements
+    int row_begin, row_stride; // local row of blockIdx.y == 0 and distance between consecutive blockIdx.y
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// "ldg" family: one thread per node, plain coalesced loads (x+-1 shifted reads are unaligned-but-contiguous per
+// warp and are absorbed by L1/L2), aligned stores.  Template flags: dtype, collision, GATHER (false for the first
+// launch after an upload: the buffer then holds pre-collision `fin`), MACROS (store rho,u), MODE.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int COLL, bool GATHER, bool MACROS, int MODE>
+__global__ void __launch_bounds__(256) lbm_step_ldg(const StepArgs a) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.nx) return;
+    const int yl = a.row_begin + blockIdx.y * a.row_stride;
+    const int b = blockIdx.z;
+    const int y = a.y0 + yl;
+    const bool left = (x == 0), right = (x == a.nx - 1), lid = (y == 0), bot = (y == a.ny - 1);
+    const T* __restrict__ src = static_cast<const T*>(a.src) + (long long)b * a.cavity;
+    T* __restrict__ dst = static_cast<T*>(a.dst) + (long long)b * a.cavity;
+    const long long P = a.plane;
+    const long long rc = (long long)(yl + 1) * a.pitch + x;   // this node
+    const long long ru = rc - a.pitch;                         // row y-1 (towards the lid)
+    const long long rd = rc + a.pitch;                         // row y+1
+    const Rates<T> r(a.cav[b]);
+
+    T f[9];
+    if (GATHER) {
+        // pull: f_k arrives from (x - c_kx, y + c_ky)
+        f[0] = src[rc];
+        f[1] = left ? (T)0 : src[1 * P + rc - 1];
+        f[2] = bot ? (T)0 : src[2 * P + rd];
+        f[3] = right ? (T)0 : src[3 * P + rc + 1];
+        f[4] = lid ? (T)0 : src[4 * P + ru];
+        f[5] = (left || bot) ? (T)0 : src[5 * P + rd - 1];
+        f[6] = (right || bot) ? (T)0 : src[6 * P + rd + 1];
+        f[7] = (right || lid) ? (T)0 : src[7 * P + ru + 1];
+        f[8] = (left || lid) ? (T)0 : src[8 * P + ru - 1];
+        if (left || right || lid || bot) {
+            const int slot = corner_slot(left, right, lid, bot);
+            T* carry = static_cast<T*>(a.carry) + b * 4;
+            const T stale = slot >= 0 ? carry[slot] : (T)0;
+            const T rl = lid ? static_cast<const T*>(a.rho_lid)[(long long)b * a.pitch + x] : (T)1;
+            wall_rule<T>(f, left, right, lid, bot, rl, r.uLB, stale);
+            if (MODE == MODE_STEP && slot >= 0) carry[slot] = corner_value<T>(f, slot);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) f[k] = src[k * P + rc];
+    }
+
+    if (MODE == MODE_FINALIZE) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dst[k * P + rc] = f[k];
+        return;
+    }
+
+    T rho, ux, uy;
+    if (MODE == MODE_MACROS) {
+        // current-state moments with the reference's overrides, no collision
+        T jx, jy;
+        moments_ref<T>(f, rho, jx, jy);
+        ux = jx / rho; uy = jy / rho;
+        if (left || right || bot) { ux = (T)0; uy = (T)0; }
+        if (lid) { rho = rho_lid_formula<T>(f); ux = r.uLB; uy = (T)0; }
+    } else {
+        node_update<T, COLL, MACROS>(f, r, left, right, lid, bot, rho, ux, uy);
+        if (lid) static_cast<T*>(a.rho_lid)[(long long)b * a.pitch + x] = rho;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dst[k * P + rc] = f[k];
+    }
+    if (MACROS || MODE == MODE_MACROS) {
+        const long long m = (long long)b * a.mplane + (long long)yl * a.pitch + x;
+        static_cast<T*>(a.rho)[m] = rho;
+        static_cast<T*>(a.ux)[m] = ux;
+        static_cast<T*>(a.uy)[m] = uy;
+    }
+}
+
+// Equilibrium start (MRT_GPU.py:259-267): rho = 1, u = (uLB, 0) on row y == 0, evaluated in fp64 then cast
+// (the reference builds it in fp64 NumPy and casts to fp32, :298).  Also seeds the corner carries and rho = 1, u = 0.
+template <typename T>
+__global__ void lbm_init_eq(StepArgs a) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.nx) return;
+    const int yl = blockIdx.y, b = blockIdx.z;
+    const int y = a.y0 + yl;
+    const double ux = (y == 0) ? a.cav[b].uLB : 0.0;
+    double fe[9];
+    feq_all<double>(1.0, ux, 0.0, fe);
+    T* dst = static_cast<T*>(a.dst) + (long long)b * a.cavity;
+    const long long rc = (long long)(yl + 1) * a.pitch + x;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dst[k * a.plane + rc] = (T)fe[k];
+    const long long m = (long long)b * a.mplane + (long long)yl * a.pitch + x;
+    static_cast<T*>(a.rho)[m] = (T)1;
+    static_cast<T*>(a.ux)[m] = (T)0;
+    static_cast<T*>(a.uy)[m] = (T)0;
+    const bool left = (x == 0), right = (x == a.nx - 1), lid = (y == 0), bot = (y == a.ny - 1);
+    const int slot = corner_slot(left, right, lid, bot);
+    if (slot >= 0) static_cast<T*>(a.carry)[b * 4 + slot] = (T)corner_value<double>(fe, slot);
+}
+
+// After an upload: seed the corner carries from the uploaded `fin` (stale ftemp slot == fin slot, MRT_GPU.py:324).
+template <typename T>
+__global__ void lbm_seed_carry(StepArgs a) {
+    const int b = blockIdx.x, slot = threadIdx.x;
+    if (slot >= 4) return;
+    const bool lid = slot < 2, left = (slot == 0 || slot == 2);
+    const int y = lid ? 0 : a.ny - 1;
+    const int yl = y - a.y0;
+    if (yl < 0 || yl >= a.nyl) return;
+    const int x = left ? 0 : a.nx - 1;
+    const T* src = static_cast<const T*>(a.src) + (long long)b * a.cavity;
+    static_cast<T*>(a.carry)[b * 4 + slot] = src[corner_pop(slot) * a.plane + (long long)(yl + 1) * a.pitch + x];
+}
+
+template <typename T>
+__global__ void lbm_fill(T* p, long long n, T v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+// Layout change between the reference's host arrays [plane][nx][ny_local] (y fastest) and device planes
+// [plane][row][pitch] (x fastest) -- the transposes of MRT_GPU.py:283-289 / 758-760, as a 32x32 shared-memory tile.
+// dev_plane(p) = dev + p_off(p); TO_DEVICE: host layout -> device layout.
+template <typename T, bool TO_DEVICE>
+__global__ void lbm_transpose(T* __restrict__ dev, T* __restrict__ lin, int nx, int nyl, int pitch,
+                              long long dev_plane_stride, long long dev_row0) {
+    __shared__ T tile[32][33];
+    const int p = blockIdx.z;
+    T* d = dev + (long long)p * dev_plane_stride + dev_row0;
+    T* l = lin + (long long)p * nx * nyl;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    if (TO_DEVICE) {
+        for (int i = threadIdx.y; i < 32; i += blockDim.y) {          // read lin[x][y], y fastest
+            const int x = x0 + i, y = y0 + threadIdx.x;
+            if (x < nx && y < nyl) tile[i][threadIdx.x] = l[(long long)x * nyl + y];
+        }
+        __syncthreads();
+        for (int i = threadIdx.y; i < 32; i += blockDim.y) {          // write dev[y][x], x fastest
+            const int y = y0 + i, x = x0 + threadIdx.x;
+            if (x < nx && y < nyl) d[(long long)y * pitch + x] = tile[threadIdx.x][i];
+        }
+    } else {
+        for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+            const int y = y0 + i, x = x0 + threadIdx.x;
+            if (x < nx && y < nyl) tile[i][threadIdx.x] = d[(long long)y * pitch + x];
+        }
+        __syncthreads();
+        for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+            const int x = x0 + i, y = y0 + threadIdx.x;
+            if (x < nx && y < nyl) l[(long long)x * nyl + y] = tile[threadIdx.x][i];
+        }
+    }
+}
+
+// functions.equ (functions.pyx:229-267): feq[k][i] from rho[i], ux[i], uy[i]
+template <typename T>
+__global__ void lbm_equ_kernel(const T* __restrict__ rho, const T* __restrict__ ux, const T* __restrict__ uy,
+                               T* __restrict__ feq, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        T fe[9];
+        feq_all<T>(rho[i], ux[i], uy[i], fe);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) feq[k * n + i] = fe[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// solver object
+// ------------------------------------------------------------------------------------------------------------
+struct lbm_solver {
+    lbm_config_t cfg{};
+    int device = 0;
+    int esz = 8;
+    int pitch = 0, nyl = 0;
+    long long plane = 0, cavity = 0, mplane = 0;
+    size_t state_bytes = 0;
+    void* f[2] = {nullptr, nullptr};
+    bool own_f = true;
+    int cur = 0;               // buffer read by the next step
+    bool pre = true;           // cur holds pre-collision `fin` (just uploaded / initialised)
+    void* rho = nullptr;       // [batch][nyl][pitch]
+    void* ux = nullptr;
+    void* uy = nullptr;
+    void* rho_lid = nullptr;
+    void* carry = nullptr;
+    CavityParams* cav = nullptr;
+    std::vector<CavityParams> cav_host;
+    bool cav_dirty = true;
+    void* staging = nullptr;   // host-layout staging for uploads/downloads
+    size_t staging_bytes = 0;
+    void* scratch = nullptr;   // finalize target (populations) when B must stay intact
+    int64_t steps = 0, launches = 0;
+    int engine = LBM_ENGINE_LDG;
+};
+
+static int set_device(lbm_solver* s) {
+    CK(cudaSetDevice(s->device));
+    return LBM_OK;
+}
+
+static StepArgs make_args(lbm_solver* s, const void* src, void* dst) {
+    StepArgs a{};
+    a.src = src; a.dst = dst;
+    a.rho = s->rho; a.ux = s->ux; a.uy = s->uy;
+    a.rho_lid = s->rho_lid; a.carry = s->carry; a.cav = s->cav;
+    a.nx = s->cfg.nx; a.ny = s->cfg.ny; a.y0 = s->cfg.y0; a.nyl = s->nyl; a.pitch = s->pitch;
+    a.plane = s->plane; a.cavity = s->cavity; a.mplane = s->mplane;
+    a.row_begin = 0; a.row_stride = 1;
+    return a;
+}
+
+static int sync_params(lbm_solver* s, cudaStream_t st) {
+    if (!s->cav_dirty) return LBM_OK;
+    CK(cudaMemcpyAsync(s->cav, s->cav_host.data(), sizeof(CavityParams) * s->cav_host.size(),
+                       cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));   // cav_host may be modified again by the caller right away
+    s->cav_dirty = false;
+    return LBM_OK;
+}
+
+// ---- kernel dispatch ----------------------------------------------------------------------------------------
+template <typename T, int COLL, bool GATHER, bool MACROS, int MODE>
+static void launch_ldg(const StepArgs& a, dim3 grid, cudaStream_t st) {
+    lbm_step_ldg<T, COLL, GATHER, MACROS, MODE><<<grid, 256, 0, st>>>(a);
+}
+
+template <typename T, int COLL>
+static void dispatch_flags(const StepArgs& a, dim3 grid, cudaStream_t st, bool gather, bool macros, int mode) {
+    if (mode == MODE_FINALIZE) { launch_ldg<T, COLL, true, false, MODE_FINALIZE>(a, grid, st); return; }
+    if (mode == MODE_MACROS) {
+        if (gather) launch_ldg<T, COLL, true, true, MODE_MACROS>(a, grid, st);
+        else launch_ldg<T, COLL, false, true, MODE_MACROS>(a, grid, st);
+        return;
+    }
+    if (gather) {
+        if (macros) launch_ldg<T, COLL, true, true, MODE_STEP>(a, grid, st);
+        else launch_ldg<T, COLL, true, false, MODE_STEP>(a, grid, st);
+    } else {
+        if (macros) launch_ldg<T, COLL, false, true, MODE_STEP>(a, grid, st);
+        else launch_ldg<T, COLL, false, false, MODE_STEP>(a, grid, st);
+    }
+}
+
+template <typename T>
+static void dispatch_coll(int coll, const StepArgs& a, dim3 grid, cudaStream_t st, bool gather, bool macros, int mode) {
+    if (mode != MODE_STEP) { dispatch_flags<T, COLL_MRT>(a, grid, st, gather, macros, mode); return; }
+    switch (coll) {
+        case LBM_SRT: dispatch_flags<T, COLL_SRT>(a, grid, st, gather, macros, mode); break;
+        case LBM_TRT: dispatch_flags<T, COLL_TRT>(a, grid, st, gather, macros, mode); break;
+        default: dispatch_flags<T, COLL_MRT>(a, grid, st, gather, macros, mode); break;
+    }
+}
+
+// Launch one pass over a row region. rows: begin, count, stride.
+static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin, int row_count, int row_stride,
+                       bool gather, bool macros, int mode, cudaStream_t st) {
+    if (row_count <= 0) return LBM_OK;
+    StepArgs a = make_args(s, src, dst);
+    a.row_begin = row_begin; a.row_stride = row_stride;
+    dim3 grid((s->cfg.nx + 255) / 256, row_count, s->cfg.batch);
+    if (grid.y > 65535u || grid.z > 65535u) {
+        // split over rows in chunks the grid can express
+        const int chunk = 65535;
+        for (int off = 0; off < row_count; off += chunk) {
+            const int n = row_count - off < chunk ? row_count - off : chunk;
+            int rc = launch_pass(s, src, dst, row_begin + off * row_stride, n, row_stride, gather, macros, mode, st);
+            if (rc) return rc;
+        }
+        return LBM_OK;
+    }
+    if (s->cfg.dtype == LBM_F64) dispatch_coll<double>(s->cfg.collision, a, grid, st, gather, macros, mode);
+    else dispatch_coll<float>(s->cfg.collision, a, grid, st, gather, macros, mode);
+    s->launches++;
+    CK(cudaGetLastError());
+    return LBM_OK;
+}
+
+static int region_rows(lbm_solver* s, int region, int rows[2][3], int* n) {
+    // rows[i] = {begin, count, stride}
+    const int nyl = s->nyl;
+    *n = 0;
+    if (region == LBM_REGION_ALL) {
+        rows[0][0] = 0; rows[0][1] = nyl; rows[0][2] = 1; *n = 1;
+    } else if (region == LBM_REGION_EDGE) {
+        if (nyl == 1) { rows[0][0] = 0; rows[0][1] = 1; rows[0][2] = 1; }
+        else { rows[0][0] = 0; rows[0][1] = 2; rows[0][2] = nyl - 1; }
+        *n = 1;
+    } else if (region == LBM_REGION_INTERIOR) {
+        rows[0][0] = 1; rows[0][1] = nyl - 2; rows[0][2] = 1; *n = 1;
+    } else {
+        return fail(LBM_EINVAL, "bad region");
+    }
+    return LBM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* lbm_last_error(void) { return g_err.c_str(); }
+int lbm_abi_version(void) { return LBM_B200_ABI_VERSION; }
+
+int lbm_device_count(int* count) {
+    if (!count) return fail(LBM_EINVAL, "count == NULL");
+    CK(cudaGetDeviceCount(count));
+    return LBM_OK;
+}
+
+static int check_cfg(const lbm_config_t* c, int* nyl_out) {
+    if (!c) return fail(LBM_EINVAL, "cfg == NULL");
+    if (c->nx < 3 || c->ny < 3) return fail(LBM_EINVAL, "nx and ny must be >= 3");
+    if (c->batch < 1) return fail(LBM_EINVAL, "batch must be >= 1");
+    if (c->dtype != LBM_F32 && c->dtype != LBM_F64) return fail(LBM_EINVAL, "dtype must be LBM_F32 or LBM_F64");
+    if (c->collision < LBM_SRT || c->collision > LBM_MRT) return fail(LBM_EINVAL, "bad collision");
+    if (c->turb != 0) return fail(LBM_EINVAL, "turb=1 (Smagorinsky) is not implemented in this build");
+    int nyl = c->ny_local == 0 ? c->ny : c->ny_local;
+    if (c->ny_local == 0 && c->y0 != 0) return fail(LBM_EINVAL, "y0 must be 0 when ny_local == 0");
+    if (c->y0 < 0 || nyl < 1 || c->y0 + nyl > c->ny) return fail(LBM_EINVAL, "y-strip [y0, y0+ny_local) outside [0, ny)");
+    if (c->engine < LBM_ENGINE_AUTO || c->engine > LBM_ENGINE_TMA) return fail(LBM_EINVAL, "bad engine");
+    *nyl_out = nyl;
+    return LBM_OK;
+}
+
+static void layout_of(const lbm_config_t* c, int nyl, lbm_layout_t* L) {
+    L->elem_size = c->dtype == LBM_F64 ? 8 : 4;
+    L->pitch = ((int64_t)c->nx + 31) / 32 * 32;
+    L->rows = nyl + 2;
+    L->plane = L->rows * L->pitch;
+    L->cavity = 9 * L->plane;
+    L->state_bytes = (int64_t)c->batch * L->cavity * L->elem_size;
+}
+
+int lbm_state_bytes(const lbm_config_t* cfg, size_t* bytes) {
+    int nyl;
+    int rc = check_cfg(cfg, &nyl);
+    if (rc) return rc;
+    if (!bytes) return fail(LBM_EINVAL, "bytes == NULL");
+    lbm_layout_t L;
+    layout_of(cfg, nyl, &L);
+    *bytes = (size_t)L.state_bytes;
+    return LBM_OK;
+}
+
+int lbm_destroy(lbm_handle_t s) {
+    if (!s) return LBM_OK;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    if (s->own_f) { cudaFree(s->f[0]); cudaFree(s->f[1]); }
+    cudaFree(s->rho); cudaFree(s->ux); cudaFree(s->uy);
+    cudaFree(s->rho_lid); cudaFree(s->carry); cudaFree(s->cav);
+    cudaFree(s->staging); cudaFree(s->scratch);
+    delete s;
+    return LBM_OK;
+}
+
+int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
+    int nyl;
+    int rc = check_cfg(cfg, &nyl);
+    if (rc) return rc;
+    if (!out) return fail(LBM_EINVAL, "out == NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(LBM_ECUDA, std::string("no usable CUDA device (there is no CPU fallback): ") +
+                                   (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    lbm_solver* s = new (std::nothrow) lbm_solver();
+    if (!s) return fail(LBM_ENOMEM, "host allocation failed");
+    s->cfg = *cfg;
+    if (cfg->device < 0) {
+        if (cudaGetDevice(&s->device) != cudaSuccess) { delete s; return fail(LBM_ECUDA, "cudaGetDevice failed"); }
+    } else {
+        s->device = cfg->device;
+    }
+    if (s->device >= ndev) { delete s; return fail(LBM_EINVAL, "device ordinal out of range"); }
+    lbm_layout_t L;
+    layout_of(cfg, nyl, &L);
+    s->esz = (int)L.elem_size; s->pitch = (int)L.pitch; s->nyl = nyl;
+    s->plane = L.plane; s->cavity = L.cavity; s->mplane = (long long)nyl * L.pitch;
+    s->state_bytes = (size_t)L.state_bytes;
+    s->engine = LBM_ENGINE_LDG;   // AUTO resolves to ldg in this build; TMA family is selected explicitly
+#define CKD(call)                                                                       \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            std::string m__ = std::string(#call) + ": " + cudaGetErrorString(e__);      \
+            lbm_destroy(s);                                                             \
+            return fail(e__ == cudaErrorMemoryAllocation ? LBM_ENOMEM : LBM_ECUDA, m__); \
+        }                                                                               \
+    } while (0)
+    CKD(cudaSetDevice(s->device));
+    if (cfg->ext_f[0] && cfg->ext_f[1]) {
+        s->f[0] = cfg->ext_f[0]; s->f[1] = cfg->ext_f[1]; s->own_f = false;
+    } else {
+        s->own_f = true;
+        CKD(cudaMalloc(&s->f[0], s->state_bytes));
+        CKD(cudaMalloc(&s->f[1], s->state_bytes));
+    }
+    // ghost rows and pitch padding must hold finite values: they are read (and discarded) by masked lanes only in
+    // the TMA family, but zero them once for determinism.
+    CKD(cudaMemset(s->f[0], 0, s->state_bytes));
+    CKD(cudaMemset(s->f[1], 0, s->state_bytes));
+    const size_t mbytes = (size_t)cfg->batch * s->mplane * s->esz;
+    CKD(cudaMalloc(&s->rho, mbytes));
+    CKD(cudaMalloc(&s->ux, mbytes));
+    CKD(cudaMalloc(&s->uy, mbytes));
+    CKD(cudaMemset(s->rho, 0, mbytes)); CKD(cudaMemset(s->ux, 0, mbytes)); CKD(cudaMemset(s->uy, 0, mbytes));
+    CKD(cudaMalloc(&s->rho_lid, (size_t)cfg->batch * s->pitch * s->esz));
+    CKD(cudaMemset(s->rho_lid, 0, (size_t)cfg->batch * s->pitch * s->esz));
+    CKD(cudaMalloc(&s->carry, (size_t)cfg->batch * 4 * s->esz));
+    CKD(cudaMemset(s->carry, 0, (size_t)cfg->batch * 4 * s->esz));
+    CKD(cudaMalloc(&s->cav, sizeof(CavityParams) * cfg->batch));
+#undef CKD
+    s->cav_host.resize(cfg->batch);
+    *out = s;
+    // defaults of the reference GPU script: Re = 100 placeholder, uLB = 0.08 (MRT_GPU.py:58)
+    rc = lbm_set_reynolds(s, -1, 0.08, 100.0);
+    if (rc) { lbm_destroy(s); *out = nullptr; return rc; }
+    return LBM_OK;
+}
+
+int lbm_get_layout(lbm_handle_t s, lbm_layout_t* out) {
+    if (!s || !out) return fail(LBM_EINVAL, "NULL argument");
+    layout_of(&s->cfg, s->nyl, out);
+    return LBM_OK;
+}
+
+int lbm_set_rates(lbm_handle_t s, int cavity, double uLB, double omega_nu, double omega_e, double omega_eps,
+                  double omega_q, double omega_minus) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    if (cavity < -1 || cavity >= s->cfg.batch) return fail(LBM_EINVAL, "cavity index out of range");
+    if (!(omega_nu > 0.0 && omega_nu < 2.0)) return fail(LBM_EINVAL, "omega_nu must lie in (0, 2)");
+    const int b0 = cavity < 0 ? 0 : cavity, b1 = cavity < 0 ? s->cfg.batch : cavity + 1;
+    for (int b = b0; b < b1; ++b) {
+        CavityParams& p = s->cav_host[b];
+        p.uLB = uLB; p.omega = omega_nu; p.omegam = omega_minus;
+        p.s_e = omega_e; p.s_eps = omega_eps; p.s_q = omega_q;
+    }
+    s->cav_dirty = true;
+    return LBM_OK;
+}
+
+int lbm_set_reynolds(lbm_handle_t s, int cavity, double uLB, double Re) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    if (!(Re > 0.0)) return fail(LBM_EINVAL, "Re must be positive");
+    const double nuLB = uLB * s->cfg.ny / Re;                 // functions.pyx:41, MRT_GPU.py:63
+    const double omega = 2.0 / (6. * nuLB + 1);               // functions.pyx:43, MRT_GPU.py:65
+    const double delTRT = 1.0 / 3.5;                          // MRT_GPU.py:83
+    const double omegam = 1.0 / (0.5 + (delTRT / ((1 / omega) - 0.5)));   // MRT_GPU.py:84
+    return lbm_set_rates(s, cavity, uLB, omega, 1.0, 1.2, 1.2, omegam);   // MRT_GPU.py:88-91
+}
+
+int lbm_init_equilibrium(lbm_handle_t s) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    int rc = set_device(s);
+    if (rc) return rc;
+    rc = sync_params(s, 0);
+    if (rc) return rc;
+    StepArgs a = make_args(s, nullptr, s->f[0]);
+    dim3 grid((s->cfg.nx + 255) / 256, 1, s->cfg.batch);
+    for (int off = 0; off < s->nyl; off += 65535) {
+        // blockIdx.y covers rows [off, off+n): shift through y0/dst offsets is avoided by a small loop
+        const int n = s->nyl - off < 65535 ? s->nyl - off : 65535;
+        StepArgs b = a;
+        b.y0 = a.y0 + off;
+        b.dst = (char*)a.dst + (size_t)off * s->pitch * s->esz;
+        b.rho = (char*)a.rho + (size_t)off * s->pitch * s->esz;
+        b.ux = (char*)a.ux + (size_t)off * s->pitch * s->esz;
+        b.uy = (char*)a.uy + (size_t)off * s->pitch * s->esz;
+        grid.y = n;
+        if (s->cfg.dtype == LBM_F64) lbm_init_eq<double><<<grid, 256>>>(b);
+        else lbm_init_eq<float><<<grid, 256>>>(b);
+        s->launches++;
+    }
+    CK(cudaGetLastError());
+    s->cur = 0; s->pre = true; s->steps = 0;
+    return LBM_OK;
+}
+
+static int ensure_staging(lbm_solver* s, size_t bytes) {
+    if (s->staging_bytes >= bytes) return LBM_OK;
+    if (s->staging) { CK(cudaFree(s->staging)); s->staging = nullptr; s->staging_bytes = 0; }
+    CK(cudaMalloc(&s->staging, bytes));
+    s->staging_bytes = bytes;
+    return LBM_OK;
+}
+
+// Move `ncav` cavities of `planes` [nx][nyl] planes each between a reference-layout array (`lin`: host, or device
+// when on_device) and device planes.  lin_cavity_bytes: distance between cavities in `lin`; dev_*_stride in elements;
+// dev_row0: element offset of local row 0 inside a device plane.
+static int move_planes(lbm_solver* s, void* lin_base, size_t lin_cavity_bytes, bool on_device, bool to_device,
+                       int ncav, int planes, void* dev_base, long long dev_plane_stride, long long dev_cavity_stride,
+                       long long dev_row0, cudaStream_t st) {
+    const int nx = s->cfg.nx, nyl = s->nyl;
+    const size_t cav_bytes = (size_t)planes * nx * nyl * s->esz;
+    dim3 blk(32, 8), grid((nx + 31) / 32, (nyl + 31) / 32, planes);
+    if (!on_device) { int rc = ensure_staging(s, cav_bytes); if (rc) return rc; }
+    for (int b = 0; b < ncav; ++b) {
+        char* h = (char*)lin_base + (size_t)b * lin_cavity_bytes;
+        void* lin = on_device ? (void*)h : s->staging;
+        char* dev = (char*)dev_base + (size_t)b * dev_cavity_stride * s->esz;
+        if (to_device && !on_device) CK(cudaMemcpyAsync(lin, h, cav_bytes, cudaMemcpyHostToDevice, st));
+        if (s->esz == 8) {
+            if (to_device) lbm_transpose<double, true><<<grid, blk, 0, st>>>((double*)dev, (double*)lin, nx, nyl, s->pitch, dev_plane_stride, dev_row0);
+            else lbm_transpose<double, false><<<grid, blk, 0, st>>>((double*)dev, (double*)lin, nx, nyl, s->pitch, dev_plane_stride, dev_row0);
+        } else {
+            if (to_device) lbm_transpose<float, true><<<grid, blk, 0, st>>>((float*)dev, (float*)lin, nx, nyl, s->pitch, dev_plane_stride, dev_row0);
+            else lbm_transpose<float, false><<<grid, blk, 0, st>>>((float*)dev, (float*)lin, nx, nyl, s->pitch, dev_plane_stride, dev_row0);
+        }
+        s->launches++;
+        CK(cudaGetLastError());
+        if (!to_device && !on_device) CK(cudaMemcpyAsync(h, lin, cav_bytes, cudaMemcpyDeviceToHost, st));
+        if (!on_device && b + 1 < ncav) CK(cudaStreamSynchronize(st));   // staging is reused by the next cavity
+    }
+    if (!on_device) CK(cudaStreamSynchronize(st));
+    return LBM_OK;
+}
+
+int lbm_upload_f(lbm_handle_t s, const void* f, int on_device, void* stream) {
+    if (!s || !f) return fail(LBM_EINVAL, "NULL argument");
+    int rc = set_device(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = sync_params(s, st);
+    if (rc) return rc;
+    const size_t fcav = (size_t)9 * s->cfg.nx * s->nyl * s->esz;
+    rc = move_planes(s, const_cast<void*>(f), fcav, on_device != 0, true, s->cfg.batch, 9, s->f[0], s->plane, s->cavity,
+                     s->pitch, st);
+    if (rc) return rc;
+    StepArgs a = make_args(s, s->f[0], nullptr);
+    if (s->esz == 8) lbm_seed_carry<double><<<s->cfg.batch, 4, 0, st>>>(a);
+    else lbm_seed_carry<float><<<s->cfg.batch, 4, 0, st>>>(a);
+    const long long n = (long long)s->cfg.batch * s->mplane;
+    if (s->esz == 8) {
+        lbm_fill<double><<<1024, 256, 0, st>>>((double*)s->rho, n, 1.0);
+        lbm_fill<double><<<1024, 256, 0, st>>>((double*)s->ux, n, 0.0);
+        lbm_fill<double><<<1024, 256, 0, st>>>((double*)s->uy, n, 0.0);
+    } else {
+        lbm_fill<float><<<1024, 256, 0, st>>>((float*)s->rho, n, 1.0f);
+        lbm_fill<float><<<1024, 256, 0, st>>>((float*)s->ux, n, 0.0f);
+        lbm_fill<float><<<1024, 256, 0, st>>>((float*)s->uy, n, 0.0f);
+    }
+    s->launches += 4;
+    CK(cudaGetLastError());
+    s->cur = 0; s->pre = true; s->steps = 0;
+    return LBM_OK;
+}
+
+int lbm_download_f(lbm_handle_t s, void* f, int on_device, void* stream) {
+    if (!s || !f) return fail(LBM_EINVAL, "NULL argument");
+    int rc = set_device(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = sync_params(s, st);
+    if (rc) return rc;
+    void* fin = s->f[s->cur];
+    if (!s->pre) {
+        // gather + wall rule (no collision) into the buffer the next step will overwrite anyway
+        void* dst = s->f[s->cur ^ 1];
+        rc = launch_pass(s, s->f[s->cur], dst, 0, s->nyl, 1, true, false, MODE_FINALIZE, st);
+        if (rc) return rc;
+        fin = dst;
+    }
+    const size_t fcav = (size_t)9 * s->cfg.nx * s->nyl * s->esz;
+    return move_planes(s, f, fcav, on_device != 0, false, s->cfg.batch, 9, fin, s->plane, s->cavity, s->pitch, st);
+}
+
+int lbm_step_region(lbm_handle_t s, int region, int write_macros, void* stream) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    int rc = set_device(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = sync_params(s, st);
+    if (rc) return rc;
+    int rows[2][3], n;
+    rc = region_rows(s, region, rows, &n);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+        rc = launch_pass(s, s->f[s->cur], s->f[s->cur ^ 1], rows[i][0], rows[i][1], rows[i][2], !s->pre,
+                         write_macros != 0, MODE_STEP, st);
+        if (rc) return rc;
+    }
+    return LBM_OK;
+}
+
+int lbm_swap(lbm_handle_t s) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    s->cur ^= 1; s->pre = false; s->steps++;
+    return LBM_OK;
+}
+
+int lbm_buffer_ptr(lbm_handle_t s, int which, void** ptr) {
+    if (!s || !ptr) return fail(LBM_EINVAL, "NULL argument");
+    *ptr = s->f[which ? (s->cur ^ 1) : s->cur];
+    return LBM_OK;
+}
+
+int lbm_step(lbm_handle_t s, int nsteps, int write_macros, void* stream) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    if (nsteps < 0) return fail(LBM_EINVAL, "nsteps < 0");
+    if (s->nyl != s->cfg.ny && nsteps > 1)
+        return fail(LBM_ESTATE, "a y-strip handle needs a halo exchange between steps: use lbm_step_region/lbm_swap");
+    for (int i = 0; i < nsteps; ++i) {
+        int rc = lbm_step_region(s, LBM_REGION_ALL, (write_macros && i == nsteps - 1) ? 1 : 0, stream);
+        if (rc) return rc;
+        lbm_swap(s);
+    }
+    return LBM_OK;
+}
+
+static int macros_out(lbm_solver* s, void* rho, void* u, int on_device, cudaStream_t st) {
+    const size_t pl = (size_t)s->cfg.nx * s->nyl * s->esz;   // one [nx][nyl] plane
+    int rc;
+    if (rho) {
+        rc = move_planes(s, rho, pl, on_device != 0, false, s->cfg.batch, 1, s->rho, s->mplane, s->mplane, 0, st);
+        if (rc) return rc;
+    }
+    if (u) {   // u[b][0] = ux, u[b][1] = uy
+        rc = move_planes(s, u, 2 * pl, on_device != 0, false, s->cfg.batch, 1, s->ux, s->mplane, s->mplane, 0, st);
+        if (rc) return rc;
+        rc = move_planes(s, (char*)u + pl, 2 * pl, on_device != 0, false, s->cfg.batch, 1, s->uy, s->mplane, s->mplane, 0, st);
+        if (rc) return rc;
+    }
+    return LBM_OK;
+}
+
+int lbm_get_macros(lbm_handle_t s, void* rho, void* u, int on_device, void* stream) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    int rc = set_device(s);
+    if (rc) return rc;
+    return macros_out(s, rho, u, on_device, (cudaStream_t)stream);
+}
+
+int lbm_get_macros_current(lbm_handle_t s, void* rho, void* u, int on_device, void* stream) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    int rc = set_device(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = sync_params(s, st);
+    if (rc) return rc;
+    rc = launch_pass(s, s->f[s->cur], s->f[s->cur ^ 1], 0, s->nyl, 1, !s->pre, true, MODE_MACROS, st);
+    if (rc) return rc;
+    return macros_out(s, rho, u, on_device, st);
+}
+
+int lbm_equilibrium(int dtype, int64_t n, const void* rho, const void* ux, const void* uy, void* feq, int on_device,
+                    void* stream) {
+    if (dtype != LBM_F32 && dtype != LBM_F64) return fail(LBM_EINVAL, "bad dtype");
+    if (n < 0 || !rho || !ux || !uy || !feq) return fail(LBM_EINVAL, "bad argument");
+    if (n == 0) return LBM_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(LBM_ECUDA, "no usable CUDA device (there is no CPU fallback)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t esz = dtype == LBM_F64 ? 8 : 4;
+    void* d = nullptr;
+    const void *dr = rho, *dx = ux, *dy = uy;
+    void* df = feq;
+    if (!on_device) {
+        CK(cudaMalloc(&d, 12 * n * esz));
+        char* c = (char*)d;
+        CK(cudaMemcpyAsync(c, rho, n * esz, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c + n * esz, ux, n * esz, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c + 2 * n * esz, uy, n * esz, cudaMemcpyHostToDevice, st));
+        dr = c; dx = c + n * esz; dy = c + 2 * n * esz; df = c + 3 * n * esz;
+    }
+    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    if (dtype == LBM_F64) lbm_equ_kernel<double><<<blocks, 256, 0, st>>>((const double*)dr, (const double*)dx, (const double*)dy, (double*)df, n);
+    else lbm_equ_kernel<float><<<blocks, 256, 0, st>>>((const float*)dr, (const float*)dx, (const float*)dy, (float*)df, n);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && !on_device) {
+        e = cudaMemcpyAsync(feq, df, 9 * n * esz, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (d) cudaFree(d);
+    if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("lbm_equilibrium: ") + cudaGetErrorString(e));
+    return LBM_OK;
+}
+
+int lbm_sync(lbm_handle_t s) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    int rc = set_device(s);
+    if (rc) return rc;
+    CK(cudaDeviceSynchronize());
+    return LBM_OK;
+}
+
+int lbm_get_counters(lbm_handle_t s, int64_t* steps_done, int64_t* kernel_launches) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    if (steps_done) *steps_done = s->steps;
+    if (kernel_launches) *kernel_launches = s->launches;
+    return LBM_OK;
+}
+
+const char* lbm_engine_name(lbm_handle_t s) {
+    if (!s) return "";
+    return s->engine == LBM_ENGINE_TMA ? "tma" : "ldg";
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+// Per-node arithmetic of the fused D2Q9 step (device code shared by every kernel family).
+//
+// Semantics "C" of the reference, executable spec = oracle/lbm_oracle.py step_C_pull:
+//   gather (pull) + wall rule      <- MRT_GPU.py:654-656 (push) + funBC :664-692
+//   moments + wall/lid overrides   <- MRT_GPU.py:615-631
+//   collision SRT / TRT / MRT      <- MRT_GPU.py:413 / :455-462,514-527 / :633-648,655
+// Index convention: y == 0 is the lid; a population with c_y = +1 moves to y-1 (MRT_GPU.py:413 "j-c").
+//   k : 0      1      2      3       4       5      6       7        8
+//   c : (0,0)  (1,0)  (0,1)  (-1,0)  (0,-1)  (1,1)  (-1,1)  (-1,-1)  (1,-1)      (MRT.py:138)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lbm {
+
+enum { COLL_SRT = 0, COLL_TRT = 1, COLL_MRT = 2 };
+enum { MODE_STEP = 0, MODE_FINALIZE = 1, MODE_MACROS = 2 };
+
+// Per-cavity rates, kept in double on the device and converted by each thread (uniform, cached loads).
+struct CavityParams {
+    double uLB;
+    double omega;      // SRT omega / TRT omega+ / MRT omega_nu   (MRT_GPU.py:65, 82, 88)
+    double omegam;     // TRT omega-                              (MRT_GPU.py:84)
+    double s_e, s_eps, s_q;                                    // (MRT_GPU.py:89-91)
+    double pad[2];
+};
+
+template <typename T>
+struct Rates {
+    T uLB, omega, omegam, s_e, s_eps, s_q;
+    __device__ __forceinline__ explicit Rates(const CavityParams& p)
+        : uLB((T)p.uLB), omega((T)p.omega), omegam((T)p.omegam), s_e((T)p.s_e), s_eps((T)p.s_eps), s_q((T)p.s_q) {}
+};
+
+// Lattice weights t_k (MRT.py:144-146).
+template <typename T> __device__ __forceinline__ T w_rest() { return (T)(4.0 / 9.0); }
+template <typename T> __device__ __forceinline__ T w_axis() { return (T)(1.0 / 9.0); }
+template <typename T> __device__ __forceinline__ T w_diag() { return (T)(1.0 / 36.0); }
+
+// feq_k = rho*t_k*(1. + 3.0*cu + 9*0.5*cu*cu - 3.0*0.5*usqr), operation order of MRT_GPU.py:651.
+template <typename T>
+__device__ __forceinline__ T feq_one(T rho, T tk, T cu, T usqr) {
+    return rho * tk * ((T)1.0 + (T)3.0 * cu + (T)4.5 * cu * cu - (T)1.5 * usqr);
+}
+
+template <typename T>
+__device__ __forceinline__ void feq_all(T rho, T ux, T uy, T fe[9]) {
+    const T usqr = ux * ux + uy * uy;
+    fe[0] = feq_one(rho, w_rest<T>(), (T)0, usqr);
+    fe[1] = feq_one(rho, w_axis<T>(), ux, usqr);
+    fe[2] = feq_one(rho, w_axis<T>(), uy, usqr);
+    fe[3] = feq_one(rho, w_axis<T>(), -ux, usqr);
+    fe[4] = feq_one(rho, w_axis<T>(), -uy, usqr);
+    fe[5] = feq_one(rho, w_diag<T>(), ux + uy, usqr);
+    fe[6] = feq_one(rho, w_diag<T>(), -ux + uy, usqr);
+    fe[7] = feq_one(rho, w_diag<T>(), -ux - uy, usqr);
+    fe[8] = feq_one(rho, w_diag<T>(), ux - uy, usqr);
+}
+
+// Wall rule on the post-stream populations f of a wall node (funBC, MRT_GPU.py:674-692): x-block, then y-block,
+// the y-block seeing the x-block's results at corners.  feq is that of the node's own previous-step state:
+// u = 0 on the three resting walls (all differences exactly 0 -> on-node bounce-back), (uLB,0) and rho_lid on y == 0.
+// `stale` is the previous final value of the doubly-orphaned corner population (persistent ftemp in the reference).
+template <typename T>
+__device__ __forceinline__ void wall_rule(T f[9], bool left, bool right, bool lid, bool bot,
+                                          T rho_lid, T uLB, T stale) {
+    T fe[9];
+    if (lid) {
+        feq_all<T>(rho_lid, uLB, (T)0, fe);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) fe[k] = (T)0;
+    }
+    if (left && lid) f[7] = stale;
+    if (right && lid) f[8] = stale;
+    if (left && bot) f[6] = stale;
+    if (right && bot) f[5] = stale;
+    if (left) {
+        f[1] = fe[1] - fe[3] + f[3];
+        f[5] = fe[5] - fe[7] + f[7];
+        f[8] = fe[8] - fe[6] + f[6];
+    } else if (right) {
+        f[3] = -fe[1] + fe[3] + f[1];
+        f[6] = -fe[8] + fe[6] + f[8];
+        f[7] = -fe[5] + fe[7] + f[5];
+    }
+    if (bot) {
+        f[2] = -fe[4] + fe[2] + f[4];
+        f[5] = -fe[7] + fe[5] + f[7];
+        f[6] = -fe[8] + fe[6] + f[8];
+    } else if (lid) {
+        f[4] = -fe[2] + fe[4] + f[2];
+        f[7] = -fe[5] + fe[7] + f[5];
+        f[8] = -fe[6] + fe[8] + f[6];
+    }
+}
+
+// Which corner-carry slot a node owns (-1 = none): 0 f7@(0,0), 1 f8@(nx-1,0), 2 f6@(0,ny-1), 3 f5@(nx-1,ny-1).
+__device__ __forceinline__ int corner_slot(bool left, bool right, bool lid, bool bot) {
+    if (lid) return left ? 0 : (right ? 1 : -1);
+    if (bot) return left ? 2 : (right ? 3 : -1);
+    return -1;
+}
+__device__ __forceinline__ int corner_pop(int slot) { return slot == 0 ? 7 : slot == 1 ? 8 : slot == 2 ? 6 : 5; }
+// f[corner_pop(slot)] without dynamic indexing (keeps f[] in registers)
+template <typename T>
+__device__ __forceinline__ T corner_value(const T f[9], int slot) {
+    return slot == 0 ? f[7] : slot == 1 ? f[8] : slot == 2 ? f[6] : f[5];
+}
+
+// rho and momentum in the reference's summation order (MRT_GPU.py:615-619).
+template <typename T>
+__device__ __forceinline__ void moments_ref(const T f[9], T& rho, T& jx, T& jy) {
+    rho = f[0] + f[1] + f[2] + f[3] + f[4] + f[5] + f[6] + f[7] + f[8];
+    jx = f[1] - f[3] + f[5] - f[6] - f[7] + f[8];
+    jy = f[2] - f[4] + f[5] + f[6] - f[7] - f[8];
+}
+
+// Lid density, MRT_GPU.py:627.
+template <typename T>
+__device__ __forceinline__ T rho_lid_formula(const T f[9]) {
+    return f[0] + f[1] + f[3] + (T)2 * (f[2] + f[5] + f[6]);
+}
+
+// ---- collisions ---------------------------------------------------------------------------------------------
+// SRT: f - omega (f - feq)   (MRT_GPU.py:413)
+template <typename T>
+__device__ __forceinline__ void collide_srt(T f[9], T rho, T ux, T uy, T omega) {
+    T fe[9];
+    feq_all<T>(rho, ux, uy, fe);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f[k] = f[k] - omega * (f[k] - fe[k]);
+}
+
+// TRT: f - omega+ (f+ - feq+) - omega- (f- - feq-)   (MRT_GPU.py:455-462, 514-527)
+template <typename T>
+__device__ __forceinline__ void collide_trt(T f[9], T rho, T ux, T uy, T omegap, T omegam) {
+    T fe[9];
+    feq_all<T>(rho, ux, uy, fe);
+    const T h = (T)0.5;
+    f[0] = f[0] - omegap * (f[0] - fe[0]) - omegam * ((T)0 - (T)0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int a = (i < 2) ? i + 1 : i + 3;     // a = 1, 2, 5, 6
+        const int o = a + 2;                       // 1<->3, 2<->4, 5<->7, 6<->8
+        const T fp = h * (f[a] + f[o]), fm = h * (f[a] - f[o]);
+        const T ep = h * (fe[a] + fe[o]), em = h * (fe[a] - fe[o]);
+        const T fa = f[a] - omegap * (fp - ep) - omegam * (fm - em);
+        const T fo = f[o] - omegap * (fp - ep) - omegam * (-fm - (-em));
+        f[a] = fa;
+        f[o] = fo;
+    }
+}
+
+// MRT in the Gram-Schmidt basis of MRT_GPU.py:593-612 with the reference's (non-standard) equilibrium moments
+// (:636-644: momentum not velocity, +9 jx^2 jy^2, cubic heat-flux terms) and rates s = [0,s_e,s_eps,0,s_q,0,s_q,s_nu,s_nu].
+// Evaluated as f* = f - Minv * S * (m - m_eq) with M and Minv hand-factored (entries 0,+-1,+-2,+-4 / 1/4..1/36):
+// ~80 flops instead of two dense 9x9 products.  Rounding differs from the reference's "Minv * m*" form at the
+// 1e-16 level per step (measured 5e-14 in rho after 1000 steps at 96^2, Re 3200; tolerance 1e-12).
+template <typename T>
+__device__ __forceinline__ void collide_mrt(T f[9], T rho, T s_e, T s_eps, T s_q, T s_nu) {
+    const T p13 = f[1] + f[3], m13 = f[1] - f[3];
+    const T p24 = f[2] + f[4], m24 = f[2] - f[4];
+    const T s57 = f[5] + f[7], d57 = f[5] - f[7];
+    const T s68 = f[6] + f[8], d68 = f[6] - f[8];
+    const T dg = s57 + s68;
+    const T jxd = d57 - d68, jyd = d57 + d68;
+    const T pxy = s57 - s68;
+    const T ab = p13 + p24;
+    const T jx = m13 + jxd, jy = m24 + jyd;
+    const T e = (T)2 * dg - ab - (T)4 * f[0];
+    const T eps = (T)4 * f[0] - (T)2 * ab + dg;
+    const T qx = jxd - (T)2 * m13, qy = jyd - (T)2 * m24;
+    const T pxx = p13 - p24;
+    const T jx2 = jx * jx, jy2 = jy * jy, sq = jx2 + jy2;
+    const T e_eq = (T)3 * sq - (T)2 * rho;
+    const T eps_eq = rho - (T)3 * sq + (T)9 * (jx2 * jy2);
+    const T qx_eq = jx * ((T)3 * jx2 - (T)1);
+    const T qy_eq = jy * ((T)3 * jy2 - (T)1);
+    const T pxx_eq = jx2 - jy2, pxy_eq = jx * jy;
+    const T de = s_e * (e - e_eq);
+    const T dp = s_eps * (eps - eps_eq);
+    const T dqx = s_q * (qx - qx_eq), dqy = s_q * (qy - qy_eq);
+    const T dxx = s_nu * (pxx - pxx_eq), dxy = s_nu * (pxy - pxy_eq);
+    const T c0 = (de - dp) * (T)(1.0 / 9.0);
+    const T cax = (de + (T)2 * dp) * (T)(1.0 / 36.0);
+    const T cdg = -((T)2 * de + dp) * (T)(1.0 / 36.0);
+    const T qx6 = dqx * (T)(1.0 / 6.0), qy6 = dqy * (T)(1.0 / 6.0);
+    const T qx12 = dqx * (T)(1.0 / 12.0), qy12 = dqy * (T)(1.0 / 12.0);
+    const T xx4 = dxx * (T)0.25, xy4 = dxy * (T)0.25;
+    const T ax_m = cax - xx4, ax_p = cax + xx4;
+    const T dg_m = cdg - xy4, dg_p = cdg + xy4;
+    const T qs = qx12 + qy12, qd = qx12 - qy12;
+    f[0] = f[0] + c0;
+    f[1] = f[1] + (ax_m + qx6);
+    f[3] = f[3] + (ax_m - qx6);
+    f[2] = f[2] + (ax_p + qy6);
+    f[4] = f[4] + (ax_p - qy6);
+    f[5] = f[5] + (dg_m - qs);
+    f[6] = f[6] + (dg_p + qd);
+    f[7] = f[7] + (dg_m + qs);
+    f[8] = f[8] + (dg_p - qd);
+}
+
+// Everything after the gather for one node: overrides, optional macro output values, collision in place.
+// Returns rho (lid-overridden) and the output velocity through the references.
+template <typename T, int COLL, bool NEED_U>
+__device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left, bool right, bool lid, bool bot,
+                                            T& rho_out, T& ux_out, T& uy_out) {
+    T rho, jx, jy;
+    moments_ref<T>(f, rho, jx, jy);
+    T ux = (T)0, uy = (T)0;
+    if (NEED_U || COLL != COLL_MRT) {
+        ux = jx / rho;
+        uy = jy / rho;
+    }
+    if (left || right || bot) { ux = (T)0; uy = (T)0; }
+    if (lid) {
+        rho = rho_lid_formula<T>(f);
+        ux = r.uLB;
+        uy = (T)0;
+    }
+    rho_out = rho; ux_out = ux; uy_out = uy;
+    if (COLL == COLL_SRT) collide_srt<T>(f, rho, ux, uy, r.omega);
+    else if (COLL == COLL_TRT) collide_trt<T>(f, rho, ux, uy, r.omega, r.omegam);
+    else collide_mrt<T>(f, rho, r.s_e, r.s_eps, r.s_q, r.omega);
+}
+
+}  // namespace lbm

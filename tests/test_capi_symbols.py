@@ -1,0 +1,79 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports exactly what include/lbm_b200.h
+declares, the ctypes mirror lists the same symbols, and the product fails loudly (no CPU fallback) without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "lbm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lbm_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from latticeboltzmannsimulations_b200 import _capi
+    lib = _capi.load()
+    names = _header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(_capi.SYMBOLS) == names
+    assert lib.lbm_abi_version() == 1
+
+
+def test_config_struct_matches_header_size():
+    from latticeboltzmannsimulations_b200 import _capi
+    assert ctypes.sizeof(_capi.Config) == 10 * 4 + 2 * 8
+    assert ctypes.sizeof(_capi.Layout) == 6 * 8
+
+
+def test_argument_validation_without_gpu():
+    from latticeboltzmannsimulations_b200 import _capi
+    lib = _capi.load()
+    cfg = _capi.Config(nx=2, ny=64, batch=1, dtype=1, collision=2, turb=0, y0=0, ny_local=0, device=-1, engine=0)
+    n = ctypes.c_size_t()
+    assert lib.lbm_state_bytes(ctypes.byref(cfg), ctypes.byref(n)) == _capi.LBM_EINVAL
+    assert b"nx" in lib.lbm_last_error()
+    cfg.nx = 100
+    assert lib.lbm_state_bytes(ctypes.byref(cfg), ctypes.byref(n)) == 0
+    assert n.value == 9 * (64 + 2) * 128 * 8          # pitch rounded up to 128, one ghost row each side
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point must raise, never silently compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import latticeboltzmannsimulations_b200 as L
+    from latticeboltzmannsimulations_b200 import functions
+    with pytest.raises(L.LBMError):
+        L.run_cavity(32, 32, 100, steps=1)
+    with pytest.raises(L.LBMError):
+        functions.equ(np.ones((4, 4)), np.zeros((4, 4)), np.zeros((4, 4)))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "latticeboltzmannsimulations_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), fn
+                assert "lbm_oracle" not in txt.replace("oracle/lbm_oracle.py", ""), fn
+
+
+def test_functions_shim_signature_errors():
+    """Same error behaviour as the Cython module for a wrong dtype."""
+    from latticeboltzmannsimulations_b200 import functions
+    with pytest.raises(ValueError, match="Buffer dtype mismatch, expected 'double_t'"):
+        functions.allfunc(np.ones((4, 4), np.float32), np.zeros((2, 4, 4)), np.zeros((9, 4, 4)), np.zeros((9, 4, 4)))
+    with pytest.raises(TypeError):
+        functions.set_omega(0.08, 100.5, 64)
+    functions.set_omega(0.08, 100.0, 64)
+    assert abs(functions.omega - 2.0 / (6 * 0.08 * 64 / 100 + 1)) < 1e-16

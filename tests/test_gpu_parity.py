@@ -1,0 +1,223 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle and the committed golden vectors.
+
+Tolerances (north star): fp64 -- max-abs difference <= 1e-12 relative, fp32 -- <= 1e-5 relative, where "relative"
+means: rho against the mean density 1, both velocity components against the lid speed uLB (the velocity scale of
+the problem), populations against 1.  The fp64 oracle is the reference for both dtypes."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import lbm_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL = {"float64": 1e-12, "float32": 1e-5}
+
+
+def errs(rho, u, f, rho0, u0, f0, uLB=0.08):
+    return (float(np.abs(rho - rho0).max()), float(np.abs(u - u0).max() / uLB),
+            float(np.abs(f - f0).max()) if f is not None else 0.0)
+
+
+def assert_close(got, want, dtype, uLB=0.08, what=""):
+    e = errs(*got, *want, uLB=uLB)
+    assert max(e) <= TOL[dtype], "%s: err rho %.3e u/uLB %.3e f %.3e (tol %.1e)" % (what, *e, TOL[dtype])
+    return e
+
+
+def _golden(name):
+    d = np.load(os.path.join(GOLDEN, name))
+    nx, ny, Re, n, uLB = d["meta"]
+    return d, int(nx), int(ny), float(Re), int(n), float(uLB)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", sorted(os.path.basename(f) for f in glob.glob(os.path.join(GOLDEN, "C_*_turb0_*.npz"))))
+def test_golden_vectors(name, dtype):
+    import latticeboltzmannsimulations_b200 as L
+    d, nx, ny, Re, n, uLB = _golden(name)
+    coll = name.split("_")[1]
+    rho, u, f = L.run_cavity(nx, ny, Re, uLB, steps=n, collision=coll, dtype=dtype, return_f=True)
+    assert_close((rho, u, f), (d["rho"], d["u"], d["fin"]), dtype, uLB, name)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("coll", ["MRT", "SRT"])
+def test_random_state_golden(coll, dtype):
+    """Generic (non-equilibrium) uploaded state: every moment and every boundary class carries signal."""
+    import latticeboltzmannsimulations_b200 as L
+    d, nx, ny, Re, n, uLB = _golden("C_%s_random_24x20_N3.npz" % coll)
+    f0 = d["f0"].astype(dtype)
+    rho, u, f = L.run_cavity(nx, ny, Re, uLB, steps=n, collision=coll, dtype=dtype, f0=f0, return_f=True)
+    assert_close((rho, u, f), (d["rho"], d["u"], d["fin"]), dtype, uLB, coll)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("coll,nx,ny,Re,n", [
+    ("MRT", 96, 64, 400, 100), ("MRT", 33, 47, 100, 10), ("MRT", 128, 128, 1000, 1000),
+    ("SRT", 64, 96, 100, 200), ("TRT", 64, 64, 400, 200), ("MRT", 257, 65, 1000, 50)])
+def test_against_live_oracle(coll, nx, ny, Re, n, dtype):
+    import latticeboltzmannsimulations_b200 as L
+    p = O.Params(nx, ny, Re=Re, collision=coll)
+    want = O.run(p, n, semantics="C", form="pull")
+    got = L.run_cavity(nx, ny, Re, steps=n, collision=coll, dtype=dtype, return_f=True)
+    assert_close(got, want, dtype, what="%s %dx%d N=%d" % (coll, nx, ny, n))
+
+
+@pytest.mark.parametrize("n", [1, 2, 10])
+def test_single_steps_every_boundary_class(n):
+    """Per boundary class (interior, 4 edges, 4 corners) after 1, 2, 10 steps from a random state."""
+    import latticeboltzmannsimulations_b200 as L
+    nx, ny = 20, 28
+    f0 = O.random_state(nx, ny, seed=5)
+    p = O.Params(nx, ny, Re=400, collision="MRT")
+    want = O.run(p, n, fin0=f0, form="push")
+    got = L.run_cavity(nx, ny, 400, steps=n, f0=f0, return_f=True)
+    classes = {"interior": (slice(1, -1), slice(1, -1)), "left": (0, slice(1, -1)), "right": (-1, slice(1, -1)),
+               "lid": (slice(1, -1), 0), "bottom": (slice(1, -1), -1), "TL": (0, 0), "TR": (-1, 0),
+               "BL": (0, -1), "BR": (-1, -1)}
+    for name, (sx, sy) in classes.items():
+        e = float(np.abs(got[2][:, sx, sy] - want[2][:, sx, sy]).max())
+        assert e <= 1e-12, (name, e)
+    assert_close(got, want, "float64")
+
+
+def test_config2_parity_384_Re3200():
+    """BASELINE config 2: 384x384, Re 3200, fp64, N in {1, 10, 100, 1000} against the oracle."""
+    import latticeboltzmannsimulations_b200 as L
+    nx = ny = 384
+    p = O.Params(nx, ny, Re=3200, collision="MRT")
+    ps = O.PullState.from_fin(O.init_fields(nx, ny, 0.08)[2], p)
+    done = 0
+    with L.CavitySolver(nx, ny, 1, "float64", "MRT") as s:
+        s.set_reynolds(3200, 0.08)
+        s.init_equilibrium()
+        for n in (1, 10, 100, 1000):
+            while done < n:
+                O.step_C_pull(ps, p)
+                done += 1
+            s.step(n - s.counters()[0], write_macros=True)
+            rho, u = s.macros()
+            f = s.download_f()
+            assert_close((rho, u, f), (ps.rho, ps.u, O.fin_from_pull(ps, p)), "float64", what="N=%d" % n)
+
+
+def test_ghia_re100_128():
+    """BASELINE config 1 physics check: 128x128, Re 100, 40 000 steps, centre-lines vs Ghia et al. (Re = 100 columns).
+    Expected for C-MRT: 0.0091 / 0.0068 of uLB."""
+    import latticeboltzmannsimulations_b200 as L
+    rho, u = L.run_cavity(128, 128, 100, 0.08, steps=40000, collision="MRT", dtype="float64")
+    ex, ey = O.ghia_errors(u, 0.08, O.load_ghia())
+    assert ex < 0.015 and ey < 0.015, (ex, ey)
+    rho32, u32 = L.run_cavity(128, 128, 100, 0.08, steps=40000, collision="MRT", dtype="float32")
+    ex32, ey32 = O.ghia_errors(u32.astype(np.float64), 0.08, O.load_ghia())
+    assert ex32 < 0.015 and ey32 < 0.015, (ex32, ey32)
+
+
+def test_batch_equals_standalone():
+    """Batched sweep: every cavity of a batch equals its standalone run bit for bit."""
+    import latticeboltzmannsimulations_b200 as L
+    Re = [100.0, 400.0, 1000.0, 3200.0, 777.0]
+    f_final, u_final, feq0, Re_out = L.datagen(Re, 64, 48, steps=150, collision="MRT", dtype="float64")
+    assert f_final.shape == (5, 9, 64, 48) and u_final.shape == (5, 2, 64, 48) and feq0.shape == (9, 64, 48)
+    for b, r in enumerate(Re):
+        rho, u, f = L.run_cavity(64, 48, r, steps=150, collision="MRT", dtype="float64", return_f=True)
+        assert np.array_equal(f, f_final[b]) and np.array_equal(u, u_final[b])
+    assert np.array_equal(feq0, O.init_fields(64, 48, 0.08)[2])
+
+
+def test_split_runs_and_reupload_are_bit_identical():
+    """steps(a) ; steps(b) == steps(a+b), and download -> upload -> continue changes nothing (fp64, bit exact)."""
+    import latticeboltzmannsimulations_b200 as L
+    nx, ny = 80, 56
+    ref = L.run_cavity(nx, ny, 1000, steps=120, return_f=True)
+    with L.CavitySolver(nx, ny) as s:
+        s.set_reynolds(1000)
+        s.init_equilibrium()
+        s.step(50)
+        s.step(70)
+        rho, u = s.macros()
+        assert np.array_equal(s.download_f(), ref[2]) and np.array_equal(u, ref[1]) and np.array_equal(rho, ref[0])
+    with L.CavitySolver(nx, ny) as s:
+        s.set_reynolds(1000)
+        s.init_equilibrium()
+        s.step(50)
+        f = s.download_f()
+        s.upload_f(f)
+        s.step(70)
+        assert np.array_equal(s.download_f(), ref[2])
+
+
+def test_current_macros_are_moments_of_f():
+    import latticeboltzmannsimulations_b200 as L
+    nx, ny = 48, 40
+    with L.CavitySolver(nx, ny) as s:
+        s.set_reynolds(400)
+        s.init_equilibrium()
+        s.step(30)
+        f = s.download_f()
+        rho, u = s.macros(current=True)
+    p = O.Params(nx, ny, Re=400)
+    r0, ux, uy = O._moments_overrides(f, p)
+    assert np.abs(rho - r0).max() <= 1e-14 and np.abs(u - np.stack([ux, uy])).max() <= 1e-15
+
+
+def test_functions_shim_matches_oracle_and_compiled_reference():
+    """`functions.allfunc` drop-in (MRT_cython.py:210,232,453 call pattern) against oracle C-SRT and, on interior
+    nodes, against the output of the compiled reference Cython module (golden ref_allfunc_*.npz)."""
+    from latticeboltzmannsimulations_b200 import functions
+    d, nx, ny, Re, n, uLB = _golden("ref_allfunc_32x24_Re100.npz")
+    f0 = O.random_state(nx, ny, seed=1234)
+    functions.set_omega(uLB, int(Re), ny)
+    u = np.zeros((2, nx, ny)); feq = np.zeros((9, nx, ny))
+    rho, u2, fin, feq2 = functions.allfunc(np.ones((nx, ny)), u, f0.copy(), feq)
+    assert u2 is u and feq2 is feq and fin is not f0
+    assert np.abs(rho - d["rho"]).max() <= 1e-15 and np.abs(u - d["u"]).max() <= 1e-15
+    assert np.abs(feq - d["feq"]).max() <= 1e-15
+    assert np.abs(fin - d["fin"])[:, 1:-1, 1:-1].max() <= 1e-15
+    p = O.Params(nx, ny, uLB=uLB, Re=Re, collision="SRT")
+    st = O.StateC.initial(p, f0)
+    O.step_C(st, p)
+    assert np.abs(fin - st.fin).max() <= 1e-15
+    # the driver pattern of MRT_cython.py: equ once, set_omega once, allfunc per iteration
+    vel = np.zeros((2, nx, ny)); vel[0, :, 0] = uLB
+    fin = functions.equ(np.ones((nx, ny)), vel[0], vel[1])
+    assert np.abs(fin - O.equ(np.ones((nx, ny)), vel)).max() <= 1e-16
+    rho = np.sum(fin, axis=0); u = np.zeros((2, nx, ny)); feq = fin.copy()
+    for _ in range(20):
+        rho, u, fin, feq = functions.allfunc(rho, u, fin, feq)
+    want = O.run(p, 20, form="push")
+    assert_close((rho, u, fin), want, "float64", uLB)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_full_size_properties_4096(dtype):
+    """BASELINE config 3 size (4096^2, Re 5000): size-independent properties instead of an oracle run --
+    determinism of split runs, mass drift bound, lid row velocity, left/right wall no-slip, finite fields."""
+    import latticeboltzmannsimulations_b200 as L
+    n = 4096
+    with L.CavitySolver(n, n, 1, dtype, "MRT") as s:
+        s.set_reynolds(5000)
+        s.init_equilibrium()
+        s.step(25)
+        s.step(25)
+        rho, u = s.macros()
+        f = s.download_f()
+    with L.CavitySolver(n, n, 1, dtype, "MRT") as s:
+        s.set_reynolds(5000)
+        s.init_equilibrium()
+        s.step(50)
+        f2 = s.download_f()
+    assert np.array_equal(f, f2)
+    assert np.isfinite(f).all()
+    assert abs(float(f.astype(np.float64).sum()) / (n * n) - 1.0) < 1e-4
+    assert np.all(u[0, :, 0] == np.asarray(0.08, dtype=dtype)) and np.all(u[:, 0, 1:] == 0) and np.all(u[:, -1, 1:] == 0)
+    # a 64-column window next to the left wall must equal a small-cavity oracle run only where causality allows:
+    # information travels one node per step, so after 50 steps nodes within 50 of the top-left corner depend only on
+    # the walls x=0, y=0 -- identical to the same nodes of a 256x256 cavity.
+    p = O.Params(256, 256, Re=5000 * 256 / 4096, collision="MRT")      # same omega: nu = uLB*ny/Re
+    want = O.run(p, 50, form="pull")[2]
+    tol = TOL[dtype]
+    assert np.abs(f[:, :100, :100] - want[:, :100, :100]).max() <= tol
