@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Benchmark of the fused D2Q9 MRT collide-and-stream step (BASELINE.json metric: MLUPS + % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+Contract (one JSON line on stdout from rank 0):
+  * N = 1  -> workload "cavity4096": BASELINE config 3, 4096 x 4096 cavity, Re 5000, uLB 0.08, fp64, MRT -- the
+              "single-GPU roofline run" the metric's roofline fraction is quoted on.  (Config 2, 384^2, is L2-resident
+              and launch-bound; it is covered by the parity tests and reported under "extra".)
+  * N > 1  -> workload "cavity32768": BASELINE config 5, ONE 32768 x 32768 cavity, Re 10000, fp64, MRT, cut into N
+              y-strips with a 3-population halo exchange per interface and step over NCCL (launched by torchrun).
+  "step" = one lattice time step of the whole cavity; value = nodes * K / time / 1e6 with the populations resident
+  in HBM; inputs are far larger than L2 (2.4 GB of A/B state vs 126 MB), so no explicit flush is needed.
+  e2e    = the same metric through the public host API with HOST buffers: upload of the initial populations from
+           pinned memory + K steps + download of rho, u (the returned fields), copies inside the timed region.
+  roofline = algorithmic bytes (144 B / node fp64, 72 B fp32: 9 loads + 9 stores) / CUDA-event time per launch,
+           against the measured copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline = the reference's own Cython/OpenMP step (functions.allfunc, compiled from the reference sources into
+           oracle/_ref) on a bounded sample, timed on this box's host cores (N = 1, rank 0 only).
+  --impl reference = the reference arm: only the reference's CPU implementation, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nx, ny, Re, description)
+    "cavity4096": (4096, 4096, 5000.0, "lid-driven cavity 4096x4096 Re=5000 uLB=0.08 D2Q9 MRT (BASELINE config 3)"),
+    "cavity32768": (32768, 32768, 10000.0, "lid-driven cavity 32768x32768 Re=10000 uLB=0.08 D2Q9 MRT, y-strips (BASELINE config 5)"),
+    "cavity384": (384, 384, 3200.0, "lid-driven cavity 384x384 Re=3200 uLB=0.08 D2Q9 MRT (BASELINE config 2)"),
+}
+BYTES_PER_NODE = {"float64": 144, "float32": 72}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for _, l in self.lines]
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in rows:
+            parts = [p.strip() for p in l.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own Cython step (oracle/_ref), else the NumPy oracle port
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_step_timer(variant: str):
+    """Returns (kind, cores, fn(n, Re, steps) -> seconds) driving the CPU step exactly like MRT_cython.py:210,232,453."""
+    import numpy as np
+    from oracle import ref_harness as R
+    if R.ref_functions_built(variant):
+        F = R.load_ref_functions(variant)
+        cores = 4 if variant == "functions" else (os.cpu_count() or 1)
+
+        def run(n, Re, steps):
+            vel = np.zeros((2, n, n)); vel[0, :, 0] = 0.08
+            fin = F.equ(np.ones((n, n)), vel[0], vel[1])                # MRT_cython.py:210
+            F.set_omega(0.08, int(Re), n)                                # :232
+            rho = np.sum(fin, axis=0); u = np.zeros((2, n, n)); feq = fin.copy()
+            rho, u, fin, feq = F.allfunc(rho, u, fin, feq)               # warm-up call
+            t = time.perf_counter()
+            for _ in range(steps):
+                rho, u, fin, feq = F.allfunc(rho, u, fin, feq)           # :453
+            return time.perf_counter() - t
+        return "reference", cores, run
+    from oracle import lbm_oracle as O
+
+    def run(n, Re, steps):
+        p = O.Params(n, n, Re=Re, collision="MRT")
+        ps = O.PullState.from_fin(O.init_fields(n, n, 0.08)[2], p)
+        O.step_C_pull(ps, p)
+        t = time.perf_counter()
+        for _ in range(steps):
+            O.step_C_pull(ps, p)
+        return time.perf_counter() - t
+    return "port", 1, run
+
+
+def cpu_baseline_sample(variant: str, Re: float, budget_s: float, n: int):
+    """Time the CPU step on an n x n sample of the workload for about budget_s seconds -> cpu_baseline dict."""
+    kind, cores, run = cpu_step_timer(variant)
+    t1 = run(n, Re, 1)
+    steps = max(2, min(400, int(budget_s / max(t1, 1e-4))))
+    t = run(n, Re, steps)
+    mlups = n * n * steps / t / 1e6
+    what = ("functions.allfunc (functions.pyx:45-222, SRT, fp64) compiled from the reference sources"
+            if kind == "reference" else "NumPy oracle port (C-MRT, fp64)")
+    threads = ("4 OpenMP threads as shipped (functions.pyx:69)" if variant == "functions" else
+               "all %d host threads (num_threads literal removed: modified thread count)" % cores)
+    return {"value": round(mlups, 2), "unit": "MLUPS", "cores": cores, "kind": kind,
+            "sample": "%d steps of a %dx%d cavity Re=%g, %s, %s, host has %d logical CPUs" % (
+                steps, n, n, Re, what, threads if kind == "reference" else "1 thread", os.cpu_count() or 0)}, t, steps
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    wl = args.workload or ("cavity4096" if args.gpus == 1 else "cavity32768")
+    nx, ny, Re, desc = WORKLOADS[wl]
+    kind, cores, run = cpu_step_timer("functions_allcores")
+    # bounded sample: choose the sub-cavity so that warmup + steps calls fit in ~100 s
+    probe_n = 512
+    t_probe = run(probe_n, Re, 2) / 2
+    per_node = t_probe / (probe_n * probe_n)
+    total_calls = args.steps + args.warmup
+    n = int((100.0 / max(total_calls, 1) / per_node) ** 0.5) // 32 * 32
+    n = max(64, min(n, nx, 2048))
+    run(n, Re, max(args.warmup - 1, 0))                       # warm-up calls (run() itself adds one)
+    t = run(n, Re, args.steps)
+    mlups = n * n * args.steps / t / 1e6
+    cb = {"value": round(mlups, 2), "unit": "MLUPS", "cores": cores, "kind": kind,
+          "sample": "each step = one functions.allfunc call (reference Cython/OpenMP step, SRT fp64, all %d host "
+                    "threads) on a %dx%d sub-cavity of the workload" % (cores, n, n)}
+    out = {"impl": "reference", "metric": "MLUPS", "value": round(mlups, 2), "unit": "MLUPS", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t / args.steps * 1e3, 4),
+           "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": wl, "description": desc, "sample_grid": [n, n]},
+           "cpu_baseline": cb,
+           "e2e": {"value": round(mlups, 2), "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def time_device_steps(step_fn, sync_fn, steps, torch):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_fn()
+    e0.record()
+    step_fn(steps)
+    e1.record()
+    sync_fn()
+    return e0.elapsed_time(e1)       # ms
+
+
+def run_single_gpu(args):
+    import numpy as np
+    import torch
+    import latticeboltzmannsimulations_b200 as L
+    wl = args.workload or "cavity4096"
+    nx, ny, Re, desc = WORKLOADS[wl]
+    torch.cuda.set_device(0)
+    peak, peak_src = measured_peak()
+    stream = torch.cuda.current_stream().cuda_stream
+    results = {}
+    clocks = None
+    launches = 0
+    for dtype in ("float64", "float32"):
+        with L.CavitySolver(nx, ny, 1, dtype, "MRT", engine=args.engine) as s:
+            s.set_reynolds(Re, 0.08)
+            s.init_equilibrium()
+            s.step(args.warmup, write_macros=False, stream=stream)
+            torch.cuda.synchronize()
+            l0 = s.counters()[1]
+            sampler = ClockSampler(0)
+            if dtype == "float64":
+                sampler.start()
+                time.sleep(0.25)
+            t0 = time.time()
+            ms = time_device_steps(lambda k: s.step(k, write_macros=False, stream=stream),
+                                   torch.cuda.synchronize, args.steps, torch)
+            t1 = time.time()
+            if dtype == "float64":
+                clocks = sampler.stop(t0, t1)
+                launches = s.counters()[1] - l0
+            mlups = nx * ny * args.steps / ms / 1e3
+            gbs = mlups * BYTES_PER_NODE[dtype] / 1e3
+            results[dtype] = {"mlups": mlups, "ms_per_step": ms / args.steps, "gbs": gbs, "engine": s.engine}
+    # ---- e2e through the host API, fp64: pinned f0 upload + K steps + rho,u download -----------------------------
+    f0 = torch.empty((9, nx, ny), dtype=torch.float64, pin_memory=True).numpy()
+    rho_out = torch.empty((nx, ny), dtype=torch.float64, pin_memory=True).numpy()
+    u_out = torch.empty((2, nx, ny), dtype=torch.float64, pin_memory=True).numpy()
+    with L.CavitySolver(nx, ny, 1, "float64", "MRT", engine=args.engine) as s:
+        s.set_reynolds(Re, 0.08)
+        s.init_equilibrium()
+        s.download_f(out=f0)                       # synthetic initial populations, now in pinned host memory
+        for _ in range(2):                         # warm-up of the whole call path (staging buffers, page mapping)
+            s.upload_f(f0); s.step(3); s.macros(rho_out=rho_out, u_out=u_out)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        s.upload_f(f0)
+        s.step(args.steps, write_macros=True)
+        s.macros(rho_out=rho_out, u_out=u_out)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t
+        assert np.isfinite(rho_out).all() and abs(float(rho_out.mean()) - 1.0) < 1e-2
+    e2e = {"value": round(nx * ny * args.steps / e2e_s / 1e6, 1), "unit": "MLUPS",
+           "h2d_bytes_per_step": int(f0.nbytes / args.steps), "d2h_bytes_per_step": int((rho_out.nbytes + u_out.nbytes) / args.steps),
+           "call": "CavitySolver.upload_f(pinned f0) + step(K) + macros() -> pinned rho,u", "seconds": round(e2e_s, 4)}
+    # ---- extra: config 2 (384^2, L2-resident, launch-latency-bound) ------------------------------------------------
+    extra = {}
+    try:
+        n2, _, Re2, _ = WORKLOADS["cavity384"]
+        with L.CavitySolver(n2, n2, 1, "float64", "MRT", engine=args.engine) as s:
+            s.set_reynolds(Re2, 0.08); s.init_equilibrium(); s.step(50, write_macros=False, stream=stream)
+            ms2 = time_device_steps(lambda k: s.step(k, write_macros=False, stream=stream), torch.cuda.synchronize, 1000, torch)
+            extra["cavity384_f64_mlups"] = round(n2 * n2 * 1000 / ms2 / 1e3, 1)
+    except Exception as exc:      # pragma: no cover
+        extra["cavity384_error"] = str(exc)
+    # ---- CPU baseline (reference Cython step as shipped, bounded sample) -------------------------------------------
+    try:
+        cb, _, _ = cpu_baseline_sample("functions", Re, 12.0, 640)
+        try:
+            cb_all, _, _ = cpu_baseline_sample("functions_allcores", Re, 8.0, 640)
+            cb["all_cores_value"] = cb_all["value"]; cb["all_cores"] = cb_all["cores"]
+        except Exception:
+            pass
+    except Exception as exc:      # pragma: no cover
+        cb = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "port", "sample": "failed: %s" % exc}
+    r64, r32 = results["float64"], results["float32"]
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get("%s_float64" % wl)
+    except Exception:
+        pass
+    out = {"metric": "MLUPS", "value": round(r64["mlups"], 1), "unit": "MLUPS", "n_gpus": 1, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(r64["ms_per_step"], 5), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": wl, "description": desc, "collision": "MRT", "engine": r64["engine"],
+                      "l2": "state (2 x %.2f GB) far larger than the 126 MB L2: no flush needed" % (nx * ny * 72 / 1e9)},
+           "roofline": {"bound": "hbm", "achieved": round(r64["gbs"], 1), "peak": peak, "unit": "GB/s",
+                        "frac": round(r64["gbs"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                        "algorithmic_bytes_per_node": 144, "nodes_per_launch": nx * ny,
+                        "frac_of_nominal_8TBs": round(r64["gbs"] / 8000.0, 4)},
+           "fp32": {"value": round(r32["mlups"], 1), "ms_per_step": round(r32["ms_per_step"], 5),
+                    "roofline_achieved": round(r32["gbs"], 1), "roofline_frac": round(r32["gbs"] / peak, 4),
+                    "algorithmic_bytes_per_node": 72},
+           "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "extra": extra}
+    print(json.dumps(out), flush=True)
+
+
+def run_multi_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from latticeboltzmannsimulations_b200.distributed import StripCavity
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = args.workload or "cavity32768"
+    nx, ny, Re, desc = WORKLOADS[wl]
+    peak, peak_src = measured_peak()
+    sc = StripCavity(nx, ny, Re, 0.08, "float64", "MRT", engine=args.engine, overlap=not args.no_overlap)
+    sc.step(args.warmup)
+    sc.sync()
+    dist.barrier()
+    torch.cuda.synchronize()
+    l0 = sc.solver.counters()[1]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    t0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sc.fork_from_current_stream()
+    sc.step(args.steps)
+    sc.join_current_stream()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = sc.solver.counters()[1] - l0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    # e2e: equilibrium start is generated on the device (77 GB of populations cannot sensibly come from the host);
+    # the returned rho,u strips are downloaded to pinned host memory inside the timed region.
+    rho_out = torch.empty((nx, sc.nyl), dtype=torch.float64, pin_memory=True).numpy()
+    u_out = torch.empty((2, nx, sc.nyl), dtype=torch.float64, pin_memory=True).numpy()
+    dist.barrier(); torch.cuda.synchronize()
+    t = time.perf_counter()
+    sc.step(args.steps, write_macros=True)
+    sc.sync()
+    sc.solver.macros(rho_out=rho_out, u_out=u_out)
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t], device="cuda")
+    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t.item())
+    if rank == 0:
+        mlups = nx * ny * args.steps / ms / 1e3
+        gbs = mlups * 144 / 1e3
+        out = {"metric": "MLUPS", "value": round(mlups, 1), "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": wl, "description": desc, "collision": "MRT", "engine": sc.solver.engine,
+                          "decomposition": "%d y-strips of %d rows, 3 populations x %d values per interface and direction "
+                                           "per step over NCCL send/recv, %s" % (
+                                               world, sc.nyl, nx, "overlapped with the interior update" if sc.overlap else "not overlapped"),
+                          "note": "the N=1 line runs cavity4096 (config 3); both are HBM-bound so MLUPS per GPU is comparable",
+                          "l2": "per-GPU state far larger than L2: no flush needed"},
+               "roofline": {"bound": "hbm", "achieved": round(gbs / world, 1), "peak": peak, "unit": "GB/s",
+                            "frac": round(gbs / world / peak, 4), "traffic": None, "peak_source": peak_src,
+                            "per_gpu": True, "algorithmic_bytes_per_node": 144},
+               "e2e": {"value": round(nx * ny * args.steps / e2e_s / 1e6, 1), "unit": "MLUPS", "h2d_bytes_per_step": 0,
+                       "d2h_bytes_per_step": int((rho_out.nbytes + u_out.nbytes) * world / args.steps),
+                       "call": "StripCavity.step(K, write_macros) + macros() -> pinned rho,u strips (init generated on device)"},
+               "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(out), flush=True)
+    sc.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--engine", default="auto", choices=["auto", "ldg", "tma"])
+    ap.add_argument("--no-overlap", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.steps is None:
+        args.steps = 1000 if args.gpus == 1 else 50
+    if args.warmup is None:
+        args.warmup = 20 if args.gpus == 1 else 5
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world > 1:
+        run_multi_gpu(args, rank, world, local_rank)
+    elif args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run on this node
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    else:
+        run_single_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

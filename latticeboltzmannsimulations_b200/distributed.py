@@ -1,0 +1,228 @@
+"""Multi-GPU drivers: one process per GPU, ``torch.distributed`` (NCCL over NVLink) as plumbing.
+
+* ``StripCavity`` -- ONE large cavity cut into contiguous y-strips (rows are x-contiguous in the device layout, so a
+  strip boundary is a whole row).  The update of a row reads only rows y-1, y, y+1, hence exactly one
+  nearest-neighbour exchange per step: across each interface the three populations that cross it
+  (towards larger y: k in {4,7,8}; towards smaller y: k in {2,5,6}), ``3 * nx`` values per direction.  Per step
+  the two edge rows of the strip are updated first on a halo stream, their crossing populations are sent straight
+  from / received straight into the population buffers (row views, no pack kernels) with grouped NCCL send/recv,
+  and the interior rows are updated concurrently on the main stream.  The reference has no multi-GPU path at all
+  (single ``cuda.Device(0)``), so there is no upstream interface to mirror here.
+* ``datagen_sharded`` -- the Reynolds sweep of ``MRT_GPU_datagen.py:55-57``: independent cavities, rank r takes the
+  cavities ``r::world``; no data-path collective (results are gathered once at the end).
+
+The partition / halo bookkeeping is plain Python over ``torch`` tensors and is exercised on CPU with the ``gloo``
+backend in ``tests/test_distributed_cpu.py``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+
+UP_POPS = (2, 5, 6)      # c_y = +1: move to y-1, i.e. to the strip above (smaller y)
+DOWN_POPS = (4, 7, 8)    # c_y = -1: move to y+1, i.e. to the strip below
+
+
+def partition_rows(ny: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous strips [(y0, ny_local)] -- the first ``ny % world`` ranks get one extra row."""
+    if world < 1 or ny < world:
+        raise ValueError("need 1 <= world <= ny")
+    base, rem = divmod(ny, world)
+    out, y0 = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((y0, n))
+        y0 += n
+    return out
+
+
+def halo_plan(rank: int, world: int, nyl: int):
+    """P2P plan of one step for ``rank``: list of (kind, peer, population, stored_row).
+
+    Stored row r holds local row r-1; stored rows 0 and nyl+1 are the ghost rows.  Sends read the freshly written
+    edge rows, receives land in the ghost rows of the same (destination) buffer.
+    """
+    plan = []
+    if rank > 0:                       # interface with the strip above
+        for k in UP_POPS:
+            plan.append(("send", rank - 1, k, 1))
+        for k in DOWN_POPS:
+            plan.append(("recv", rank - 1, k, 0))
+    if rank < world - 1:               # interface with the strip below
+        for k in DOWN_POPS:
+            plan.append(("send", rank + 1, k, nyl))
+        for k in UP_POPS:
+            plan.append(("recv", rank + 1, k, nyl + 1))
+    return plan
+
+
+class HaloExchanger:
+    """Executes ``halo_plan`` on a pair of A/B buffers given as tensors ``[9, nyl+2, pitch]`` (any device/backend)."""
+
+    def __init__(self, buffers, nx: int, rank: int, world: int, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank, self.world = rank, world
+        nyl = buffers[0].shape[1] - 2
+        self.plan = halo_plan(rank, world, nyl)
+        # ops are fixed per destination buffer: build them once (views of the persistent buffers)
+        self._ops = []
+        for buf in buffers:
+            ops = []
+            for kind, peer, k, row in self.plan:
+                view = buf[k, row, :nx]
+                fn = dist.isend if kind == "send" else dist.irecv
+                ops.append(dist.P2POp(fn, view, peer, group=group))
+            self._ops.append(ops)
+
+    def exchange(self, which: int):
+        """Start the exchange on buffer ``which``; returns the work handles (call ``.wait()`` on each)."""
+        if not self._ops[which]:
+            return []
+        return self.dist.batch_isend_irecv(self._ops[which])
+
+
+class StripCavity:
+    """One cavity decomposed into y-strips over the ranks of ``group`` (one CUDA device per rank)."""
+
+    def __init__(self, nx: int, ny: int, Re: float, uLB: float = 0.08, dtype="float64", collision: str = "MRT",
+                 group=None, device: Optional[int] = None, engine: str = "auto", overlap: bool = True):
+        import torch
+        import torch.distributed as dist
+        from .solver import CavitySolver, _dtype_name
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.nx, self.ny = nx, ny
+        self.parts = partition_rows(ny, self.world)
+        self.y0, self.nyl = self.parts[self.rank]
+        self.device = torch.cuda.current_device() if device is None else device
+        tdt = torch.float64 if _dtype_name(dtype) == "float64" else torch.float32
+        nbytes = CavitySolver.state_bytes(nx, ny, 1, dtype, ny_local=self.nyl)
+        esz = 8 if tdt == torch.float64 else 4
+        with torch.cuda.device(self.device):
+            self._raw = [torch.zeros(nbytes // esz, dtype=tdt, device="cuda") for _ in range(2)]
+        self.solver = CavitySolver(nx, ny, 1, dtype, collision, y0=self.y0, ny_local=self.nyl, device=self.device,
+                                   engine=engine, ext_buffers=[t.data_ptr() for t in self._raw])
+        lay = self.solver.layout
+        self.buffers = [t.view(9, int(lay.rows), int(lay.pitch)) for t in self._raw]
+        self.solver.set_reynolds(Re, uLB)
+        self.solver.init_equilibrium()
+        self._ptr = {self._raw[0].data_ptr(): 0, self._raw[1].data_ptr(): 1}
+        self.halo = HaloExchanger(self.buffers, nx, self.rank, self.world, group)
+        self.overlap = overlap and self.nyl >= 3
+        with torch.cuda.device(self.device):
+            self.s_main = torch.cuda.Stream()
+            self.s_halo = torch.cuda.Stream(priority=-1)
+            self.ev_main = torch.cuda.Event()
+            self.ev_halo = torch.cuda.Event()
+            self.ev_main.record(torch.cuda.current_stream())
+            self.ev_halo.record(torch.cuda.current_stream())
+        self.steps_done = 0
+
+    def _dst_index(self) -> int:
+        return self._ptr[self.solver.buffer_ptr(1)]
+
+    def step(self, nsteps: int = 1, write_macros: bool = False) -> None:
+        torch = self.torch
+        s = self.solver
+        for i in range(nsteps):
+            wm = write_macros and i == nsteps - 1
+            dst = self._dst_index()
+            if self.overlap:
+                with torch.cuda.stream(self.s_halo):
+                    self.s_halo.wait_event(self.ev_main)              # interior of the previous step
+                    s.step_region(_capi.LBM_REGION_EDGE, wm, self.s_halo.cuda_stream)
+                    for w in self.halo.exchange(dst):
+                        w.wait()                                       # stream-side wait, the host runs ahead
+                    new_halo = torch.cuda.Event()
+                    new_halo.record(self.s_halo)
+                with torch.cuda.stream(self.s_main):
+                    self.s_main.wait_event(self.ev_halo)              # edge rows + halo of the previous step
+                    s.step_region(_capi.LBM_REGION_INTERIOR, wm, self.s_main.cuda_stream)
+                    new_main = torch.cuda.Event()
+                    new_main.record(self.s_main)
+                self.ev_halo, self.ev_main = new_halo, new_main
+            else:
+                with torch.cuda.stream(self.s_main):
+                    s.step_region(_capi.LBM_REGION_ALL, wm, self.s_main.cuda_stream)
+                    for w in self.halo.exchange(dst):
+                        w.wait()
+            s.swap()
+            self.steps_done += 1
+
+    def sync(self) -> None:
+        self.s_main.synchronize()
+        self.s_halo.synchronize()
+
+    def join_current_stream(self) -> None:
+        """Make the caller's current stream wait for everything issued so far (for event timing on that stream)."""
+        cur = self.torch.cuda.current_stream()
+        if self.overlap:
+            cur.wait_event(self.ev_main)
+            cur.wait_event(self.ev_halo)
+        else:
+            cur.wait_stream(self.s_main)
+
+    def fork_from_current_stream(self) -> None:
+        cur = self.torch.cuda.current_stream()
+        self.s_main.wait_stream(cur)
+        self.s_halo.wait_stream(cur)
+
+    # -- results (validation / output; not on the timed path) -----------------------------------------------------
+    def local_fields(self, current: bool = False):
+        self.sync()
+        rho, u = self.solver.macros(current=current)
+        return rho, u, self.solver.download_f()
+
+    def gather_fields(self, current: bool = False):
+        """Full-cavity (rho[nx,ny], u[2,nx,ny], f[9,nx,ny]) on rank 0 (None elsewhere)."""
+        rho, u, f = self.local_fields(current)
+        objs = [None] * self.world if self.rank == 0 else None
+        self.dist.gather_object((rho, u, f), objs, dst=0, group=self.group)
+        if self.rank != 0:
+            return None
+        return (np.concatenate([o[0] for o in objs], axis=1), np.concatenate([o[1] for o in objs], axis=2),
+                np.concatenate([o[2] for o in objs], axis=2))
+
+    def close(self) -> None:
+        self.sync()
+        self.solver.close()
+
+
+def shard_indices(n: int, rank: int, world: int) -> List[int]:
+    """Cavity b of a sweep goes to rank b mod world."""
+    return list(range(rank, n, world))
+
+
+def datagen_sharded(Re_list: Sequence[float], nx: int = 384, ny: int = 384, uLB: float = 0.08, steps: int = 10000,
+                    collision: str = "MRT", dtype="float32", group=None, gather: bool = True):
+    """Sharded sweep: each rank advances its own cavities; rank 0 assembles the reference's output arrays."""
+    import torch.distributed as dist
+    from .cavity import datagen
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = shard_indices(len(Re_list), rank, world)
+    local = datagen([Re_list[i] for i in mine], nx, ny, uLB, steps, collision, dtype) if mine else None
+    if not gather:
+        return mine, local
+    objs = [None] * world if rank == 0 else None
+    dist.gather_object((mine, local), objs, dst=0, group=group)
+    if rank != 0:
+        return None
+    n = len(Re_list)
+    npdt = np.float32 if np.dtype(dtype) == np.float32 else np.float64
+    f_final = np.empty((n, 9, nx, ny), npdt)
+    u_final = np.empty((n, 2, nx, ny), npdt)
+    feq0 = None
+    for idx, loc in objs:
+        if not idx:
+            continue
+        f_final[idx] = loc[0]
+        u_final[idx] = loc[1]
+        feq0 = loc[2] if feq0 is None else feq0
+    return f_final, u_final, feq0, np.asarray(list(Re_list), dtype=np.float64)

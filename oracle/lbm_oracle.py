@@ -444,6 +444,127 @@ def fin_from_pull(ps: PullState, p: Params) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------------
+# y-strip form of the fused pull pass (specification of the multi-GPU decomposition).
+# --------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class StripState:
+    """One y-strip [y0, y0+nyl) of a cavity in the fused-kernel representation.
+
+    ``g`` is ``[9, nx, nyl+2]``: stored row r holds local row r-1, rows 0 and nyl+1 are ghost rows that the halo
+    exchange fills with the neighbour strip's edge rows (only populations 4,7,8 of the row above and 2,5,6 of the
+    row below are ever read).  Everything else as ``PullState``.
+    """
+    g: np.ndarray
+    kind: str
+    y0: int
+    nyl: int
+    rho_lid: np.ndarray
+    carry: np.ndarray
+    rho: Optional[np.ndarray] = None
+    u: Optional[np.ndarray] = None
+
+    @staticmethod
+    def from_fin(fin0: np.ndarray, p: Params, y0: int, nyl: int) -> "StripState":
+        nx, ny = p.nx, p.ny
+        g = np.zeros((Q, nx, nyl + 2))
+        g[:, :, 1:nyl + 1] = fin0[:, :, y0:y0 + nyl]
+        carry = np.array([fin0[7, 0, 0], fin0[8, nx - 1, 0], fin0[6, 0, ny - 1], fin0[5, nx - 1, ny - 1]])
+        return StripState(g=g, kind="pre", y0=y0, nyl=nyl, rho_lid=np.zeros(nx), carry=carry)
+
+
+def _strip_gather_bc(ss: StripState, p: Params):
+    nx, ny, y0, nyl = p.nx, p.ny, ss.y0, ss.nyl
+    if ss.kind == "pre":
+        return ss.g[:, :, 1:nyl + 1].copy(), ss.carry.copy()
+    g = ss.g
+    has_lid, has_bot = (y0 == 0), (y0 + nyl == ny)
+    h = np.full((Q, nx, nyl), np.nan)
+    for k in range(Q):
+        cx, cy = int(C[k, 0]), int(C[k, 1])
+        xd = slice(max(0, cx), nx - max(0, -cx))            # destination x with 0 <= x - cx < nx
+        xs = slice(xd.start - cx, xd.stop - cx)
+        j0, j1 = 0, nyl                                     # destination local rows with 0 <= y + cy < ny
+        if cy < 0 and has_lid:
+            j0 = 1
+        if cy > 0 and has_bot:
+            j1 = nyl - 1
+        h[k, xd, j0:j1] = g[k, xs, j0 + cy + 1:j1 + cy + 1]
+    if has_lid:
+        h[7, 0, 0] = ss.carry[CARRY_TL]
+        h[8, nx - 1, 0] = ss.carry[CARRY_TR]
+    if has_bot:
+        h[6, 0, nyl - 1] = ss.carry[CARRY_BL]
+        h[5, nx - 1, nyl - 1] = ss.carry[CARRY_BR]
+    rho_w = np.ones((nx, nyl)); ux = np.zeros((nx, nyl)); uy = np.zeros((nx, nyl))
+    if has_lid:
+        rho_w[:, 0] = ss.rho_lid
+        ux[:, 0] = p.uLB
+    fe = _feq_kernel(rho_w, ux, uy)
+    x = 0
+    h[1, x, :] = fe[1, x, :] - fe[3, x, :] + h[3, x, :]
+    h[5, x, :] = fe[5, x, :] - fe[7, x, :] + h[7, x, :]
+    h[8, x, :] = fe[8, x, :] - fe[6, x, :] + h[6, x, :]
+    x = nx - 1
+    h[3, x, :] = -fe[1, x, :] + fe[3, x, :] + h[1, x, :]
+    h[6, x, :] = -fe[8, x, :] + fe[6, x, :] + h[8, x, :]
+    h[7, x, :] = -fe[5, x, :] + fe[7, x, :] + h[5, x, :]
+    if has_bot:
+        y = nyl - 1
+        h[2, :, y] = -fe[4, :, y] + fe[2, :, y] + h[4, :, y]
+        h[5, :, y] = -fe[7, :, y] + fe[5, :, y] + h[7, :, y]
+        h[6, :, y] = -fe[8, :, y] + fe[6, :, y] + h[8, :, y]
+    if has_lid:
+        y = 0
+        h[4, :, y] = -fe[2, :, y] + fe[4, :, y] + h[2, :, y]
+        h[7, :, y] = -fe[5, :, y] + fe[7, :, y] + h[5, :, y]
+        h[8, :, y] = -fe[6, :, y] + fe[8, :, y] + h[6, :, y]
+    assert not np.isnan(h).any()
+    carry = ss.carry.copy()
+    if has_lid:
+        carry[CARRY_TL], carry[CARRY_TR] = h[7, 0, 0], h[8, nx - 1, 0]
+    if has_bot:
+        carry[CARRY_BL], carry[CARRY_BR] = h[6, 0, nyl - 1], h[5, nx - 1, nyl - 1]
+    return h, carry
+
+
+def step_C_pull_strip(ss: StripState, p: Params) -> None:
+    """One launch on one strip; the caller must then exchange halo rows (see ``exchange_halo_local``)."""
+    nx, ny, y0, nyl = p.nx, p.ny, ss.y0, ss.nyl
+    h, carry = _strip_gather_bc(ss, p)
+    # moments / overrides on the strip: embed the wall tests in global coordinates
+    rho_l = _lsum([h[k] for k in range(Q)])
+    ux = _lsum([C[k, 0] * h[k] for k in range(Q)]) / rho_l
+    uy = _lsum([C[k, 1] * h[k] for k in range(Q)]) / rho_l
+    ux[0, :] = 0; uy[0, :] = 0; ux[nx - 1, :] = 0; uy[nx - 1, :] = 0
+    if y0 + nyl == ny:
+        ux[:, nyl - 1] = 0; uy[:, nyl - 1] = 0
+    if y0 == 0:
+        rho_l = rho_l.copy()
+        rho_l[:, 0] = h[0, :, 0] + h[1, :, 0] + h[3, :, 0] + 2 * (h[2, :, 0] + h[5, :, 0] + h[6, :, 0])
+        ux[:, 0] = p.uLB; uy[:, 0] = 0
+    feq = _feq_kernel(rho_l, ux, uy)
+    ss.g[:, :, 1:nyl + 1] = _collide(h, rho_l, feq, p, p.omega)
+    ss.kind = "post"
+    if y0 == 0:
+        ss.rho_lid = rho_l[:, 0].copy()
+    ss.carry = carry
+    ss.rho, ss.u = rho_l, np.stack([ux, uy])
+
+
+def exchange_halo_local(strips) -> None:
+    """In-process halo exchange between consecutive strips (what NCCL send/recv does between ranks)."""
+    for a, b in zip(strips[:-1], strips[1:]):           # a above b
+        for k in (4, 7, 8):                             # c_y = -1: cross towards larger y
+            b.g[k, :, 0] = a.g[k, :, a.nyl]
+        for k in (2, 5, 6):                             # c_y = +1: cross towards smaller y
+            a.g[k, :, a.nyl + 1] = b.g[k, :, 1]
+
+
+def strip_fin(ss: StripState, p: Params) -> np.ndarray:
+    return _strip_gather_bc(ss, p)[0]
+
+
+# --------------------------------------------------------------------------------------------
 # Drivers
 # --------------------------------------------------------------------------------------------
 def run(p: Params, steps: int, semantics: str = "C", fin0: Optional[np.ndarray] = None, form: str = "push"):

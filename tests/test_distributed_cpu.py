@@ -1,0 +1,114 @@
+"""Host-side logic of the multi-GPU paths on CPU: row partition, halo plan, and a world_size-2/3 `gloo` run in
+which every rank advances its strip with the oracle's strip form and exchanges halo rows through the SAME
+HaloExchanger the GPU path uses (CPU tensors instead of CUDA tensors) -- the result must equal the single-domain
+oracle bit for bit.  Also the cavity -> rank sharding of the batched sweep."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import lbm_oracle as O
+from latticeboltzmannsimulations_b200.distributed import (HaloExchanger, halo_plan, partition_rows,
+                                                           shard_indices, DOWN_POPS, UP_POPS)
+
+
+def test_partition_rows():
+    assert partition_rows(10, 3) == [(0, 4), (4, 3), (7, 3)]
+    assert partition_rows(32768, 8) == [(i * 4096, 4096) for i in range(8)]
+    for ny, w in [(7, 7), (100, 8), (33, 2)]:
+        parts = partition_rows(ny, w)
+        assert parts[0][0] == 0 and sum(n for _, n in parts) == ny
+        assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+    with pytest.raises(ValueError):
+        partition_rows(3, 4)
+
+
+def test_halo_plan_is_symmetric():
+    """Every send has exactly one matching recv on the peer: same population, edge row -> ghost row."""
+    world, nyl = 4, 5
+    plans = [halo_plan(r, world, nyl) for r in range(world)]
+    assert len(plans[0]) == 6 and len(plans[1]) == 12 and len(plans[3]) == 6
+    for r in range(world):
+        for kind, peer, k, row in plans[r]:
+            if kind != "send":
+                continue
+            going_up = peer == r - 1
+            assert k in (UP_POPS if going_up else DOWN_POPS)
+            assert row == (1 if going_up else nyl)
+            want_row = nyl + 1 if going_up else 0
+            assert ("recv", r, k, want_row) in plans[peer]
+    # order of sends on one side matches order of recvs on the other (NCCL/gloo match P2P ops in issue order)
+    for r in range(world - 1):
+        down = [k for kind, peer, k, _ in plans[r] if kind == "send" and peer == r + 1]
+        up_recv = [k for kind, peer, k, _ in plans[r + 1] if kind == "recv" and peer == r]
+        assert down == up_recv
+
+
+def test_shard_indices():
+    assert shard_indices(10, 1, 4) == [1, 5, 9]
+    allidx = sorted(i for r in range(8) for i in shard_indices(256, r, 8))
+    assert allidx == list(range(256)) and len(shard_indices(256, 3, 8)) == 32
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, nx, ny, steps, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p = O.Params(nx, ny, Re=400, collision="MRT")
+        fin0 = O.random_state(nx, ny, seed=3)
+        y0, nyl = partition_rows(ny, world)[rank]
+        ss = O.StripState.from_fin(fin0, p, y0, nyl)
+        pitch = (nx + 31) // 32 * 32
+        bufs = [torch.zeros(9, nyl + 2, pitch, dtype=torch.float64) for _ in range(2)]   # device layout [k][row][x]
+        ex = HaloExchanger(bufs, nx, rank, world)
+        which = 0
+        for _ in range(steps):
+            ss.g[:, :, 0] = np.nan; ss.g[:, :, nyl + 1] = np.nan       # ghosts must come from the exchange only
+            if rank > 0:
+                ss.g[:, :, 0] = bufs[which][:, 0, :nx].numpy()
+            if rank < world - 1:
+                ss.g[:, :, nyl + 1] = bufs[which][:, nyl + 1, :nx].numpy()
+            O.step_C_pull_strip(ss, p)
+            which ^= 1
+            bufs[which][:, 1:nyl + 1, :nx] = torch.from_numpy(ss.g[:, :, 1:nyl + 1].transpose(0, 2, 1).copy())
+            for w in ex.exchange(which):
+                w.wait()
+        ss.g[:, :, 0] = bufs[which][:, 0, :nx].numpy()
+        ss.g[:, :, nyl + 1] = bufs[which][:, nyl + 1, :nx].numpy()
+        out = [None] * world if rank == 0 else None
+        dist.gather_object((O.strip_fin(ss, p), ss.rho), out, dst=0)
+        if rank == 0:
+            q.put((np.concatenate([o[0] for o in out], axis=2), np.concatenate([o[1] for o in out], axis=1)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nx,ny", [(2, 24, 30), (3, 20, 23)])
+def test_strip_decomposition_gloo(world, nx, ny):
+    steps = 12
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, ny, steps, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    f, rho = q.get(timeout=120)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    p = O.Params(nx, ny, Re=400, collision="MRT")
+    want = O.run(p, steps, fin0=O.random_state(nx, ny, seed=3), form="pull")
+    assert np.array_equal(f, want[2]) and np.array_equal(rho, want[0])
