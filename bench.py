@@ -310,7 +310,9 @@ def run_multi_gpu(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+    time.sleep(0.25)                  # every rank waits alike, then all start together
+    dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
