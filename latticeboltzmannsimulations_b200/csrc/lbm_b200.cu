@@ -7,6 +7,7 @@
 // POST-collision populations; the next launch pulls them (streaming), applies the wall rule, collides and stores
 // into the other buffer.  Side buffers carry what the wall rule needs from the previous step: rho_lid[b][x] and the
 // four doubly-orphaned corner populations carry[b][4] (see oracle/lbm_oracle.py PullState).
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -18,6 +19,7 @@
 
 #include "../../include/lbm_b200.h"
 #include "lbm_device.cuh"
+#include "lbm_tma.cuh"
 
 using namespace lbm;
 
@@ -36,24 +38,6 @@ static int fail(int code, const std::string& msg) {
             return fail(e__ == cudaErrorMemoryAllocation ? LBM_ENOMEM : LBM_ECUDA,                       \
                         std::string(#call) + ": " + cudaGetErrorString(e__));                            \
     } while (0)
-
-// ------------------------------------------------------------------------------------------------------------
-// kernel arguments
-// ------------------------------------------------------------------------------------------------------------
-struct StepArgs {
-    const void* src;
-    void* dst;
-    void* rho;
-    void* ux;
-    void* uy;
-    void* rho_lid;             // [batch][pitch]
-    void* carry;               // [batch][4]
-    const CavityParams* cav;   // [batch]
-    int nx, ny, y0, nyl, pitch;
-    long long plane, cavity;   // elements
-    long long mplane;          // macro plane = nyl * pitch elements
-    int row_begin, row_stride; // local row of blockIdx.y == 0 and distance between consecutive blockIdx.y
-};
 
 // ------------------------------------------------------------------------------------------------------------
 // "ldg" family: one thread per node, plain coalesced loads (x+-1 shifted reads are unaligned-but-contiguous per
@@ -126,6 +110,144 @@ __global__ void __launch_bounds__(256) lbm_step_ldg(const StepArgs a) {
         static_cast<T*>(a.rho)[m] = rho;
         static_cast<T*>(a.ux)[m] = ux;
         static_cast<T*>(a.uy)[m] = uy;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// "ldg" family, vector form (hot path only: MODE_STEP with gather): one thread updates V consecutive nodes of a
+// row.  Every population is fetched with ONE aligned V-wide load per thread (64/128-bit, coalesced along x); the
+// x-1 / x+1 element that the pull step needs from the neighbouring thread's vector comes by warp shuffle, and only
+// the first / last lane of a warp issues one extra scalar load.  Stores are aligned V-wide.  Per node this halves
+// (V = 2) or quarters (V = 4) the load/store and address instructions of the scalar kernel.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int V> struct GVec;
+template <> struct GVec<float, 2> { using type = float2; };
+template <> struct GVec<float, 4> { using type = float4; };
+template <> struct GVec<double, 2> { using type = double2; };
+
+template <typename T, int V>
+__device__ __forceinline__ void gload(const T* p, T out[V]) {
+    using VT = typename GVec<T, V>::type;
+    const VT v = *reinterpret_cast<const VT*>(p);
+    const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) out[i] = e[i];
+}
+template <typename T, int V>
+__device__ __forceinline__ void gstore(T* p, const T in[V]) {
+    using VT = typename GVec<T, V>::type;
+    VT v;
+    T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+    for (int i = 0; i < V; ++i) e[i] = in[i];
+    *reinterpret_cast<VT*>(p) = v;
+}
+
+template <typename T, int COLL, bool MACROS, int V>
+__global__ void __launch_bounds__(256) lbm_step_vec(const StepArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * V;          // first node of this thread
+    const int yl = a.row_begin + blockIdx.y * a.row_stride;
+    const int b = blockIdx.z;
+    const int y = a.y0 + yl;
+    const bool lid = (y == 0), bot = (y == a.ny - 1);
+    const bool active = x < a.nx;                                       // whole warps may be partially outside
+    const T* __restrict__ src = static_cast<const T*>(a.src) + (long long)b * a.cavity;
+    T* __restrict__ dst = static_cast<T*>(a.dst) + (long long)b * a.cavity;
+    const long long P = a.plane;
+    // clamp the address of inactive threads to a valid one (they still take part in the shuffles)
+    const int xc = active ? x : 0;
+    const long long rc = (long long)(yl + 1) * a.pitch + xc;
+    const long long ru = rc - a.pitch, rd = rc + a.pitch;
+    const Rates<T> r(a.cav[b]);
+    const unsigned full = 0xffffffffu;
+
+    T f[V][9];
+    // aligned vectors of every population at this thread's columns, from the row the population comes from
+    T v0[V], v1[V], v2[V], v3[V], v4[V], v5[V], v6[V], v7[V], v8[V];
+    gload<T, V>(src + rc, v0);
+    gload<T, V>(src + 1 * P + rc, v1);
+    gload<T, V>(src + 2 * P + rd, v2);
+    gload<T, V>(src + 3 * P + rc, v3);
+    gload<T, V>(src + 4 * P + ru, v4);
+    gload<T, V>(src + 5 * P + rd, v5);
+    gload<T, V>(src + 6 * P + rd, v6);
+    gload<T, V>(src + 7 * P + ru, v7);
+    gload<T, V>(src + 8 * P + ru, v8);
+    // element x-1 for c_x = +1 (k = 1,5,8): previous lane's last element; lane 0 loads it (0 at the left wall)
+    T l1 = __shfl_up_sync(full, v1[V - 1], 1), l5 = __shfl_up_sync(full, v5[V - 1], 1), l8 = __shfl_up_sync(full, v8[V - 1], 1);
+    if (lane == 0) {
+        const bool ok = active && x > 0;
+        l1 = ok ? src[1 * P + rc - 1] : (T)0;
+        l5 = ok ? src[5 * P + rd - 1] : (T)0;
+        l8 = ok ? src[8 * P + ru - 1] : (T)0;
+    }
+    // element x+V for c_x = -1 (k = 3,6,7): next lane's first element; lane 31 loads it (0 beyond the right wall)
+    T h3 = __shfl_down_sync(full, v3[0], 1), h6 = __shfl_down_sync(full, v6[0], 1), h7 = __shfl_down_sync(full, v7[0], 1);
+    if (lane == 31) {
+        const bool ok = active && (x + V) < a.nx;
+        h3 = ok ? src[3 * P + rc + V] : (T)0;
+        h6 = ok ? src[6 * P + rd + V] : (T)0;
+        h7 = ok ? src[7 * P + ru + V] : (T)0;
+    }
+    if (!active) return;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        f[v][0] = v0[v];
+        f[v][2] = v2[v];
+        f[v][4] = v4[v];
+        f[v][1] = v == 0 ? l1 : v1[v - 1];
+        f[v][5] = v == 0 ? l5 : v5[v - 1];
+        f[v][8] = v == 0 ? l8 : v8[v - 1];
+        f[v][3] = v == V - 1 ? h3 : v3[v + 1];
+        f[v][6] = v == V - 1 ? h6 : v6[v + 1];
+        f[v][7] = v == V - 1 ? h7 : v7[v + 1];
+    }
+    T rho[V], ux[V], uy[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int xv = x + v;
+        const bool left = (xv == 0), right = (xv == a.nx - 1);
+        if ((left || right || lid || bot) && xv < a.nx) {
+            const int slot = corner_slot(left, right, lid, bot);
+            T* carry = static_cast<T*>(a.carry) + b * 4;
+            const T stale = slot >= 0 ? carry[slot] : (T)0;
+            const T rl = lid ? static_cast<const T*>(a.rho_lid)[(long long)b * a.pitch + xv] : (T)1;
+            wall_rule<T>(f[v], left, right, lid, bot, rl, r.uLB, stale);
+            if (slot >= 0) carry[slot] = corner_value<T>(f[v], slot);
+        }
+        node_update<T, COLL, MACROS>(f[v], r, left, right, lid, bot, rho[v], ux[v], uy[v]);
+    }
+    if (lid) {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (x + v < a.nx) static_cast<T*>(a.rho_lid)[(long long)b * a.pitch + x + v] = rho[v];
+    }
+    if (x + V <= a.nx) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            T tmp[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) tmp[v] = f[v][k];
+            gstore<T, V>(dst + k * P + rc, tmp);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (x + v < a.nx) dst[k * P + rc + v] = f[v][k];
+    }
+    if (MACROS) {
+        const long long m = (long long)b * a.mplane + (long long)yl * a.pitch + x;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            if (x + v < a.nx) {
+                static_cast<T*>(a.rho)[m + v] = rho[v];
+                static_cast<T*>(a.ux)[m + v] = ux[v];
+                static_cast<T*>(a.uy)[m + v] = uy[v];
+            }
+        }
     }
 }
 
@@ -249,6 +371,15 @@ struct lbm_solver {
     void* scratch = nullptr;   // finalize target (populations) when B must stay intact
     int64_t steps = 0, launches = 0;
     int engine = LBM_ENGINE_LDG;
+    // tma family
+    CUtensorMap tmap[2][2];    // [buffer][0 = narrow box, 1 = wide box]
+    bool tmap_ok = false;
+    int num_sms = 148;
+    int tma_variant = 0;       // index into the compiled (TY, STAGES) configurations
+    int tma_ctas_per_sm = 1;
+    // nodes per thread of the ldg family (1 = scalar kernel).  Measured at 4096^2 on B200 (tools/tma_sweep.py):
+    // fp64 scalar 47 067 vs vec2 45 905 MLUPS; fp32 scalar 87 132, vec2 88 321, vec4 91 055 MLUPS.
+    int vec_f64 = 1, vec_f32 = 4;
 };
 
 static int set_device(lbm_solver* s) {
@@ -274,6 +405,94 @@ static int sync_params(lbm_solver* s, cudaStream_t st) {
     CK(cudaStreamSynchronize(st));   // cav_host may be modified again by the caller right away
     s->cav_dirty = false;
     return LBM_OK;
+}
+
+
+// ---- tma family: tensor maps and launch ------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <typename T> struct TmaVec { static constexpr int V = 16 / sizeof(T); };
+
+// compiled tile configurations: {TY, STAGES}
+#define LBM_TMA_VARIANTS 3
+static const int kTmaTY[LBM_TMA_VARIANTS] = {4, 4, 8};      // rows per tile (fp32 tiles use twice as many rows)
+// stages per variant: {4, 3, 2}
+
+static int make_tensor_maps(lbm_solver* s) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+        return fail(LBM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    EncodeTiledFn encode = (EncodeTiledFn)fn;
+    const int V = 16 / s->esz;
+    const int ty = kTmaTY[s->tma_variant] * (s->esz == 4 ? 2 : 1);
+    const int txn = (s->esz == 8 ? 64 : 32) * V;       // TmaCfg::TX
+    cuuint64_t dims[2] = {(cuuint64_t)s->pitch, (cuuint64_t)s->cfg.batch * 9 * (cuuint64_t)(s->nyl + 2)};
+    cuuint64_t strides[1] = {(cuuint64_t)s->pitch * s->esz};
+    cuuint32_t estr[2] = {1, 1};
+    for (int i = 0; i < 2; ++i) {
+        for (int w = 0; w < 2; ++w) {
+            cuuint32_t box[2] = {(cuuint32_t)(txn + (w ? V : 0)), (cuuint32_t)ty};
+            CUresult r = encode(&s->tmap[i][w],
+                                s->esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, s->f[i],
+                                dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS)
+                return fail(LBM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        }
+    }
+    s->tmap_ok = true;
+    return LBM_OK;
+}
+
+template <typename T, int COLL, int TY, int STAGES, int MINB>
+static cudaError_t launch_tma_cfg(lbm_solver* s, const CUtensorMap* tm, const StepArgs& a, const TileSched& ts, cudaStream_t st) {
+    constexpr int V = TmaVec<T>::V;
+    using Cfg = TmaCfg<T, V, TY, STAGES>;
+    auto kern = lbm_step_tma<T, COLL, false, V, TY, STAGES, MINB>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    long long want = (long long)s->num_sms * s->tma_ctas_per_sm;
+    int grid = (int)(ts.tiles_total < want ? ts.tiles_total : want);
+    TileSched t2 = ts;
+    const int per = ts.tiles_x * ts.tiles_y;
+    t2.adv_b = grid / per;
+    t2.adv_y = (grid - t2.adv_b * per) / ts.tiles_x;
+    t2.adv_x = grid - t2.adv_b * per - t2.adv_y * ts.tiles_x;
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tm[0], tm[1], a, t2);
+    return cudaGetLastError();
+}
+
+template <typename T, int COLL>
+static cudaError_t launch_tma_variant(lbm_solver* s, const CUtensorMap* tm, const StepArgs& a, TileSched ts, cudaStream_t st) {
+    constexpr int V = TmaVec<T>::V;
+    constexpr int M = sizeof(T) == 4 ? 2 : 1;          // fp32 tiles: half as many threads per row, twice the rows
+    constexpr int TX = (sizeof(T) == 8 ? 64 : 32) * V;
+    const int ty = kTmaTY[s->tma_variant] * M;
+    ts.tiles_x = (s->cfg.nx + TX - 1) / TX;
+    ts.tiles_y = (ts.row_count + ty - 1) / ty;
+    ts.tiles_total = (long long)ts.tiles_x * ts.tiles_y * s->cfg.batch;
+    switch (s->tma_variant) {
+        case 1: return launch_tma_cfg<T, COLL, 4 * M, 3, 2>(s, tm, a, ts, st);
+        case 2: return launch_tma_cfg<T, COLL, 8 * M, 2, 1>(s, tm, a, ts, st);
+        default: return launch_tma_cfg<T, COLL, 4 * M, 4, 1>(s, tm, a, ts, st);
+    }
+}
+
+template <typename T>
+static cudaError_t launch_tma_coll(lbm_solver* s, const CUtensorMap* tm, const StepArgs& a, const TileSched& ts, cudaStream_t st) {
+    switch (s->cfg.collision) {
+        case LBM_SRT: return launch_tma_variant<T, COLL_SRT>(s, tm, a, ts, st);
+        case LBM_TRT: return launch_tma_variant<T, COLL_TRT>(s, tm, a, ts, st);
+        default: return launch_tma_variant<T, COLL_MRT>(s, tm, a, ts, st);
+    }
 }
 
 // ---- kernel dispatch ----------------------------------------------------------------------------------------
@@ -309,12 +528,39 @@ static void dispatch_coll(int coll, const StepArgs& a, dim3 grid, cudaStream_t s
     }
 }
 
+// ---- vector ldg dispatch (hot path) ---------------------------------------------------------------------------
+template <typename T, int COLL, int V>
+static void launch_vec_flags(const StepArgs& a, int nx, int rows, int batch, cudaStream_t st, bool macros) {
+    dim3 grid((nx + 256 * V - 1) / (256 * V), rows, batch);
+    if (macros) lbm_step_vec<T, COLL, true, V><<<grid, 256, 0, st>>>(a);
+    else lbm_step_vec<T, COLL, false, V><<<grid, 256, 0, st>>>(a);
+}
+template <typename T, int V>
+static void launch_vec_coll(int coll, const StepArgs& a, int nx, int rows, int batch, cudaStream_t st, bool macros) {
+    switch (coll) {
+        case LBM_SRT: launch_vec_flags<T, COLL_SRT, V>(a, nx, rows, batch, st, macros); break;
+        case LBM_TRT: launch_vec_flags<T, COLL_TRT, V>(a, nx, rows, batch, st, macros); break;
+        default: launch_vec_flags<T, COLL_MRT, V>(a, nx, rows, batch, st, macros); break;
+    }
+}
+
 // Launch one pass over a row region. rows: begin, count, stride.
 static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin, int row_count, int row_stride,
                        bool gather, bool macros, int mode, cudaStream_t st) {
     if (row_count <= 0) return LBM_OK;
     StepArgs a = make_args(s, src, dst);
     a.row_begin = row_begin; a.row_stride = row_stride;
+    if (s->engine == LBM_ENGINE_TMA && s->tmap_ok && mode == MODE_STEP && gather && !macros && row_stride == 1 &&
+        (src == s->f[0] || src == s->f[1])) {
+        TileSched ts{};
+        ts.row_begin = row_begin; ts.row_count = row_count; ts.rows_per_plane = s->nyl + 2;
+        const CUtensorMap* tm = s->tmap[src == s->f[0] ? 0 : 1];
+        cudaError_t e = s->cfg.dtype == LBM_F64 ? launch_tma_coll<double>(s, tm, a, ts, st)
+                                                : launch_tma_coll<float>(s, tm, a, ts, st);
+        s->launches++;
+        if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("tma launch: ") + cudaGetErrorString(e));
+        return LBM_OK;
+    }
     dim3 grid((s->cfg.nx + 255) / 256, row_count, s->cfg.batch);
     if (grid.y > 65535u || grid.z > 65535u) {
         // split over rows in chunks the grid can express
@@ -326,7 +572,12 @@ static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin,
         }
         return LBM_OK;
     }
-    if (s->cfg.dtype == LBM_F64) dispatch_coll<double>(s->cfg.collision, a, grid, st, gather, macros, mode);
+    const int vw = s->cfg.dtype == LBM_F64 ? s->vec_f64 : s->vec_f32;
+    if (mode == MODE_STEP && gather && vw > 1) {
+        if (s->cfg.dtype == LBM_F64) launch_vec_coll<double, 2>(s->cfg.collision, a, s->cfg.nx, row_count, s->cfg.batch, st, macros);
+        else if (vw == 4) launch_vec_coll<float, 4>(s->cfg.collision, a, s->cfg.nx, row_count, s->cfg.batch, st, macros);
+        else launch_vec_coll<float, 2>(s->cfg.collision, a, s->cfg.nx, row_count, s->cfg.batch, st, macros);
+    } else if (s->cfg.dtype == LBM_F64) dispatch_coll<double>(s->cfg.collision, a, grid, st, gather, macros, mode);
     else dispatch_coll<float>(s->cfg.collision, a, grid, st, gather, macros, mode);
     s->launches++;
     CK(cudaGetLastError());
@@ -436,7 +687,15 @@ int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
     s->esz = (int)L.elem_size; s->pitch = (int)L.pitch; s->nyl = nyl;
     s->plane = L.plane; s->cavity = L.cavity; s->mplane = (long long)nyl * L.pitch;
     s->state_bytes = (size_t)L.state_bytes;
-    s->engine = LBM_ENGINE_LDG;   // AUTO resolves to ldg in this build; TMA family is selected explicitly
+    s->engine = cfg->engine == LBM_ENGINE_TMA ? LBM_ENGINE_TMA : LBM_ENGINE_LDG;   // AUTO -> ldg
+    if (const char* ev = getenv("LBM_B200_ENGINE")) {         // development override
+        if (!strcmp(ev, "tma")) s->engine = LBM_ENGINE_TMA;
+        if (!strcmp(ev, "ldg")) s->engine = LBM_ENGINE_LDG;
+    }
+    if (const char* ev = getenv("LBM_B200_VEC_F64")) s->vec_f64 = atoi(ev) == 2 ? 2 : 1;
+    if (const char* ev = getenv("LBM_B200_VEC_F32")) s->vec_f32 = (atoi(ev) == 2 || atoi(ev) == 4) ? atoi(ev) : 1;
+    if (const char* ev = getenv("LBM_B200_TMA_VARIANT")) s->tma_variant = atoi(ev) % LBM_TMA_VARIANTS;
+    if (const char* ev = getenv("LBM_B200_TMA_CTAS")) s->tma_ctas_per_sm = atoi(ev) > 0 ? atoi(ev) : 1;
 #define CKD(call)                                                                       \
     do {                                                                                \
         cudaError_t e__ = (call);                                                       \
@@ -470,6 +729,14 @@ int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
     CKD(cudaMalloc(&s->cav, sizeof(CavityParams) * cfg->batch));
 #undef CKD
     s->cav_host.resize(cfg->batch);
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, s->device) == cudaSuccess) s->num_sms = prop.multiProcessorCount;
+    }
+    if (s->engine == LBM_ENGINE_TMA) {
+        int trc = make_tensor_maps(s);
+        if (trc) { std::string m = g_err; lbm_destroy(s); return fail(trc, m); }
+    }
     *out = s;
     // defaults of the reference GPU script: Re = 100 placeholder, uLB = 0.08 (MRT_GPU.py:58)
     rc = lbm_set_reynolds(s, -1, 0.08, 100.0);

@@ -25,6 +25,22 @@ struct CavityParams {
     double pad[2];
 };
 
+// Kernel arguments shared by every kernel family (device pointers are untyped: dtype is a template parameter).
+struct StepArgs {
+    const void* src;
+    void* dst;
+    void* rho;
+    void* ux;
+    void* uy;
+    void* rho_lid;             // [batch][pitch]
+    void* carry;               // [batch][4]
+    const CavityParams* cav;   // [batch]
+    int nx, ny, y0, nyl, pitch;
+    long long plane, cavity;   // elements
+    long long mplane;          // macro plane = nyl * pitch elements
+    int row_begin, row_stride; // local row of blockIdx.y == 0 and distance between consecutive blockIdx.y
+};
+
 template <typename T>
 struct Rates {
     T uLB, omega, omegam, s_e, s_eps, s_q;
