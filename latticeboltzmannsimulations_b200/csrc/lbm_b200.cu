@@ -380,6 +380,10 @@ struct lbm_solver {
     // nodes per thread of the ldg family (1 = scalar kernel).  Measured at 4096^2 on B200 (tools/tma_sweep.py):
     // fp64 scalar 47 067 vs vec2 45 905 MLUPS; fp32 scalar 87 132, vec2 88 321, vec4 91 055 MLUPS.
     int vec_f64 = 1, vec_f32 = 4;
+    // CUDA graphs of the steady step loop: graph[p] = 2*GRAPH_PAIRS launches starting with buffer p as source
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    cudaStream_t capture_stream = nullptr;
+    int use_graph = 1;
 };
 
 static int set_device(lbm_solver* s) {
@@ -659,6 +663,8 @@ int lbm_destroy(lbm_handle_t s) {
     cudaFree(s->rho); cudaFree(s->ux); cudaFree(s->uy);
     cudaFree(s->rho_lid); cudaFree(s->carry); cudaFree(s->cav);
     cudaFree(s->staging); cudaFree(s->scratch);
+    for (int i = 0; i < 2; ++i) if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
+    if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
     delete s;
     return LBM_OK;
 }
@@ -694,6 +700,7 @@ int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
     }
     if (const char* ev = getenv("LBM_B200_VEC_F64")) s->vec_f64 = atoi(ev) == 2 ? 2 : 1;
     if (const char* ev = getenv("LBM_B200_VEC_F32")) s->vec_f32 = (atoi(ev) == 2 || atoi(ev) == 4) ? atoi(ev) : 1;
+    if (const char* ev = getenv("LBM_B200_GRAPH")) s->use_graph = atoi(ev) != 0;
     if (const char* ev = getenv("LBM_B200_TMA_VARIANT")) s->tma_variant = atoi(ev) % LBM_TMA_VARIANTS;
     if (const char* ev = getenv("LBM_B200_TMA_CTAS")) s->tma_ctas_per_sm = atoi(ev) > 0 ? atoi(ev) : 1;
 #define CKD(call)                                                                       \
@@ -920,15 +927,58 @@ int lbm_buffer_ptr(lbm_handle_t s, int which, void** ptr) {
     return LBM_OK;
 }
 
+// Steps per graph launch (even, so a graph leaves the A/B parity unchanged).  The per-launch CPU cost of a plain
+// stream launch (~2.5 us) is what bounds small cavities such as 384^2 (kernel ~3 us); a graph of 32 steps amortises it.
+#define LBM_GRAPH_STEPS 32
+#define LBM_GRAPH_MAX_NODES (1 << 22)   // only launch-latency-bound sizes take the graph path
+
+static int build_graph(lbm_solver* s, int parity) {
+    if (!s->capture_stream) CK(cudaStreamCreateWithFlags(&s->capture_stream, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(s->capture_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = LBM_OK;
+    int cur = parity;
+    const int64_t launches0 = s->launches;
+    for (int i = 0; i < LBM_GRAPH_STEPS && rc == LBM_OK; ++i) {
+        rc = launch_pass(s, s->f[cur], s->f[cur ^ 1], 0, s->nyl, 1, true, false, MODE_STEP, s->capture_stream);
+        cur ^= 1;
+    }
+    s->launches = launches0;            // counted when the graph is launched, not when it is captured
+    cudaError_t e = cudaStreamEndCapture(s->capture_stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&s->graph[parity], g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    return LBM_OK;
+}
+
 int lbm_step(lbm_handle_t s, int nsteps, int write_macros, void* stream) {
     if (!s) return fail(LBM_EINVAL, "NULL handle");
     if (nsteps < 0) return fail(LBM_EINVAL, "nsteps < 0");
     if (s->nyl != s->cfg.ny && nsteps > 1)
         return fail(LBM_ESTATE, "a y-strip handle needs a halo exchange between steps: use lbm_step_region/lbm_swap");
-    for (int i = 0; i < nsteps; ++i) {
-        int rc = lbm_step_region(s, LBM_REGION_ALL, (write_macros && i == nsteps - 1) ? 1 : 0, stream);
+    int left = nsteps;
+    const bool small = (long long)s->cfg.nx * s->nyl * s->cfg.batch <= LBM_GRAPH_MAX_NODES;
+    while (left > 0) {
+        const bool last = (left == 1);
+        // steady state (post-collision buffer, no macro output) in blocks of LBM_GRAPH_STEPS: one graph launch
+        if (s->use_graph && small && !s->pre && left > LBM_GRAPH_STEPS) {
+            int rc = set_device(s);
+            if (rc) return rc;
+            rc = sync_params(s, (cudaStream_t)stream);
+            if (rc) return rc;
+            if (!s->graph[s->cur]) { rc = build_graph(s, s->cur); if (rc) return rc; }
+            CK(cudaGraphLaunch(s->graph[s->cur], (cudaStream_t)stream));
+            s->launches += LBM_GRAPH_STEPS;
+            s->steps += LBM_GRAPH_STEPS;
+            left -= LBM_GRAPH_STEPS;
+            continue;
+        }
+        int rc = lbm_step_region(s, LBM_REGION_ALL, (write_macros && last) ? 1 : 0, stream);
         if (rc) return rc;
         lbm_swap(s);
+        --left;
     }
     return LBM_OK;
 }
