@@ -38,8 +38,8 @@ def run_cavity(nx: int, ny: int, Re: float, uLB: float = 0.08, steps: int = 1000
 
 
 def datagen(Re_list: Sequence[float], nx: int = 384, ny: int = 384, uLB: float = 0.08, steps: int = 10000,
-            collision: str = "MRT", dtype="float32", device: Optional[int] = None, engine: str = "auto",
-            chunk: Optional[int] = None):
+            collision: str = "MRT", dtype="float32", turb: bool = False, device: Optional[int] = None,
+            engine: str = "auto", chunk: Optional[int] = None):
     """Batched Reynolds sweep of ``MRT_GPU_datagen.py``: every cavity of ``Re_list`` advanced ``steps`` steps.
 
     Returns ``(f_final[N,9,nx,ny], u_final[N,2,nx,ny], feq_initial[9,nx,ny], Re_range[N])`` in the dtype / ``[x,y]``
@@ -55,7 +55,7 @@ def datagen(Re_list: Sequence[float], nx: int = 384, ny: int = 384, uLB: float =
     chunk = n if chunk is None else max(1, int(chunk))
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)
-        with CavitySolver(nx, ny, hi - lo, dtype, collision, device=device, engine=engine) as s:
+        with CavitySolver(nx, ny, hi - lo, dtype, collision, turb, device=device, engine=engine) as s:
             s.set_reynolds(Re_arr[lo:hi], uLB)
             s.init_equilibrium()
             if feq_initial is None:

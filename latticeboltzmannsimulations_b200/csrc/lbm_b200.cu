@@ -44,7 +44,7 @@ static int fail(int code, const std::string& msg) {
 // warp and are absorbed by L1/L2), aligned stores.  Template flags: dtype, collision, GATHER (false for the first
 // launch after an upload: the buffer then holds pre-collision `fin`), MACROS (store rho,u), MODE.
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, int COLL, bool GATHER, bool MACROS, int MODE>
+template <typename T, int COLL, bool GATHER, bool MACROS, int MODE, bool TURB = false>
 __global__ void __launch_bounds__(256) lbm_step_ldg(const StepArgs a) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= a.nx) return;
@@ -100,7 +100,18 @@ __global__ void __launch_bounds__(256) lbm_step_ldg(const StepArgs a) {
         if (left || right || bot) { ux = (T)0; uy = (T)0; }
         if (lid) { rho = rho_lid_formula<T>(f); ux = r.uLB; uy = (T)0; }
     } else {
-        node_update<T, COLL, MACROS>(f, r, left, right, lid, bot, rho, ux, uy);
+        if (TURB) {
+            const long long m = (long long)b * a.mplane + (long long)yl * a.pitch + x;
+            T* pi = static_cast<T*>(a.pi_eq) + m;
+            T* rp = static_cast<T*>(a.rho_prev) + m;
+            const T om = smagorinsky_omega<T>(f, *pi, *rp, r.omega);
+            T pi_new;
+            node_update<T, COLL, MACROS, true>(f, r, left, right, lid, bot, rho, ux, uy, om, &pi_new);
+            *pi = pi_new;
+            *rp = rho;
+        } else {
+            node_update<T, COLL, MACROS>(f, r, left, right, lid, bot, rho, ux, uy);
+        }
         if (lid) static_cast<T*>(a.rho_lid)[(long long)b * a.pitch + x] = rho;
 #pragma unroll
         for (int k = 0; k < 9; ++k) dst[k * P + rc] = f[k];
@@ -273,6 +284,23 @@ __global__ void lbm_init_eq(StepArgs a) {
     const bool left = (x == 0), right = (x == a.nx - 1), lid = (y == 0), bot = (y == a.ny - 1);
     const int slot = corner_slot(left, right, lid, bot);
     if (slot >= 0) static_cast<T*>(a.carry)[b * 4 + slot] = (T)corner_value<double>(fe, slot);
+    if (a.pi_eq) {   // feq_g := fin, rho_g := 1 at start (MRT_GPU.py:325-326)
+        static_cast<T*>(a.pi_eq)[m] = (T)fe[5] - (T)fe[6] + (T)fe[7] - (T)fe[8];
+        static_cast<T*>(a.rho_prev)[m] = (T)1;
+    }
+}
+
+// After an upload with turb = 1: feq_g := uploaded fin, rho_g := 1 (MRT_GPU.py:325-326).
+template <typename T>
+__global__ void lbm_seed_turb(StepArgs a) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.nx) return;
+    const int yl = blockIdx.y, b = blockIdx.z;
+    const T* src = static_cast<const T*>(a.src) + (long long)b * a.cavity;
+    const long long rc = (long long)(yl + 1) * a.pitch + x;
+    const long long m = (long long)b * a.mplane + (long long)yl * a.pitch + x;
+    static_cast<T*>(a.pi_eq)[m] = src[5 * a.plane + rc] - src[6 * a.plane + rc] + src[7 * a.plane + rc] - src[8 * a.plane + rc];
+    static_cast<T*>(a.rho_prev)[m] = (T)1;
 }
 
 // After an upload: seed the corner carries from the uploaded `fin` (stale ftemp slot == fin slot, MRT_GPU.py:324).
@@ -363,6 +391,8 @@ struct lbm_solver {
     void* uy = nullptr;
     void* rho_lid = nullptr;
     void* carry = nullptr;
+    void* pi_eq = nullptr;     // Smagorinsky state (turb = 1 only)
+    void* rho_prev = nullptr;
     CavityParams* cav = nullptr;
     std::vector<CavityParams> cav_host;
     bool cav_dirty = true;
@@ -396,6 +426,7 @@ static StepArgs make_args(lbm_solver* s, const void* src, void* dst) {
     a.src = src; a.dst = dst;
     a.rho = s->rho; a.ux = s->ux; a.uy = s->uy;
     a.rho_lid = s->rho_lid; a.carry = s->carry; a.cav = s->cav;
+    a.pi_eq = s->pi_eq; a.rho_prev = s->rho_prev;
     a.nx = s->cfg.nx; a.ny = s->cfg.ny; a.y0 = s->cfg.y0; a.nyl = s->nyl; a.pitch = s->pitch;
     a.plane = s->plane; a.cavity = s->cavity; a.mplane = s->mplane;
     a.row_begin = 0; a.row_stride = 1;
@@ -505,6 +536,17 @@ static void launch_ldg(const StepArgs& a, dim3 grid, cudaStream_t st) {
     lbm_step_ldg<T, COLL, GATHER, MACROS, MODE><<<grid, 256, 0, st>>>(a);
 }
 
+template <typename T, int COLL, bool TURB>
+static void dispatch_step(const StepArgs& a, dim3 grid, cudaStream_t st, bool gather, bool macros) {
+    if (gather) {
+        if (macros) lbm_step_ldg<T, COLL, true, true, MODE_STEP, TURB><<<grid, 256, 0, st>>>(a);
+        else lbm_step_ldg<T, COLL, true, false, MODE_STEP, TURB><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (macros) lbm_step_ldg<T, COLL, false, true, MODE_STEP, TURB><<<grid, 256, 0, st>>>(a);
+        else lbm_step_ldg<T, COLL, false, false, MODE_STEP, TURB><<<grid, 256, 0, st>>>(a);
+    }
+}
+
 template <typename T, int COLL>
 static void dispatch_flags(const StepArgs& a, dim3 grid, cudaStream_t st, bool gather, bool macros, int mode) {
     if (mode == MODE_FINALIZE) { launch_ldg<T, COLL, true, false, MODE_FINALIZE>(a, grid, st); return; }
@@ -513,13 +555,8 @@ static void dispatch_flags(const StepArgs& a, dim3 grid, cudaStream_t st, bool g
         else launch_ldg<T, COLL, false, true, MODE_MACROS>(a, grid, st);
         return;
     }
-    if (gather) {
-        if (macros) launch_ldg<T, COLL, true, true, MODE_STEP>(a, grid, st);
-        else launch_ldg<T, COLL, true, false, MODE_STEP>(a, grid, st);
-    } else {
-        if (macros) launch_ldg<T, COLL, false, true, MODE_STEP>(a, grid, st);
-        else launch_ldg<T, COLL, false, false, MODE_STEP>(a, grid, st);
-    }
+    if (a.pi_eq) dispatch_step<T, COLL, true>(a, grid, st, gather, macros);
+    else dispatch_step<T, COLL, false>(a, grid, st, gather, macros);
 }
 
 template <typename T>
@@ -554,7 +591,7 @@ static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin,
     if (row_count <= 0) return LBM_OK;
     StepArgs a = make_args(s, src, dst);
     a.row_begin = row_begin; a.row_stride = row_stride;
-    if (s->engine == LBM_ENGINE_TMA && s->tmap_ok && mode == MODE_STEP && gather && !macros && row_stride == 1 &&
+    if (s->engine == LBM_ENGINE_TMA && s->tmap_ok && !s->cfg.turb && mode == MODE_STEP && gather && !macros && row_stride == 1 &&
         (src == s->f[0] || src == s->f[1])) {
         TileSched ts{};
         ts.row_begin = row_begin; ts.row_count = row_count; ts.rows_per_plane = s->nyl + 2;
@@ -577,7 +614,7 @@ static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin,
         return LBM_OK;
     }
     const int vw = s->cfg.dtype == LBM_F64 ? s->vec_f64 : s->vec_f32;
-    if (mode == MODE_STEP && gather && vw > 1) {
+    if (mode == MODE_STEP && gather && vw > 1 && !s->cfg.turb) {
         if (s->cfg.dtype == LBM_F64) launch_vec_coll<double, 2>(s->cfg.collision, a, s->cfg.nx, row_count, s->cfg.batch, st, macros);
         else if (vw == 4) launch_vec_coll<float, 4>(s->cfg.collision, a, s->cfg.nx, row_count, s->cfg.batch, st, macros);
         else launch_vec_coll<float, 2>(s->cfg.collision, a, s->cfg.nx, row_count, s->cfg.batch, st, macros);
@@ -626,7 +663,7 @@ static int check_cfg(const lbm_config_t* c, int* nyl_out) {
     if (c->batch < 1) return fail(LBM_EINVAL, "batch must be >= 1");
     if (c->dtype != LBM_F32 && c->dtype != LBM_F64) return fail(LBM_EINVAL, "dtype must be LBM_F32 or LBM_F64");
     if (c->collision < LBM_SRT || c->collision > LBM_MRT) return fail(LBM_EINVAL, "bad collision");
-    if (c->turb != 0) return fail(LBM_EINVAL, "turb=1 (Smagorinsky) is not implemented in this build");
+    if (c->turb != 0 && c->turb != 1) return fail(LBM_EINVAL, "turb must be 0 or 1");
     int nyl = c->ny_local == 0 ? c->ny : c->ny_local;
     if (c->ny_local == 0 && c->y0 != 0) return fail(LBM_EINVAL, "y0 must be 0 when ny_local == 0");
     if (c->y0 < 0 || nyl < 1 || c->y0 + nyl > c->ny) return fail(LBM_EINVAL, "y-strip [y0, y0+ny_local) outside [0, ny)");
@@ -662,6 +699,7 @@ int lbm_destroy(lbm_handle_t s) {
     if (s->own_f) { cudaFree(s->f[0]); cudaFree(s->f[1]); }
     cudaFree(s->rho); cudaFree(s->ux); cudaFree(s->uy);
     cudaFree(s->rho_lid); cudaFree(s->carry); cudaFree(s->cav);
+    cudaFree(s->pi_eq); cudaFree(s->rho_prev);
     cudaFree(s->staging); cudaFree(s->scratch);
     for (int i = 0; i < 2; ++i) if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
     if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
@@ -734,6 +772,12 @@ int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
     CKD(cudaMalloc(&s->carry, (size_t)cfg->batch * 4 * s->esz));
     CKD(cudaMemset(s->carry, 0, (size_t)cfg->batch * 4 * s->esz));
     CKD(cudaMalloc(&s->cav, sizeof(CavityParams) * cfg->batch));
+    if (cfg->turb) {
+        CKD(cudaMalloc(&s->pi_eq, mbytes));
+        CKD(cudaMalloc(&s->rho_prev, mbytes));
+        CKD(cudaMemset(s->pi_eq, 0, mbytes));
+        CKD(cudaMemset(s->rho_prev, 0, mbytes));
+    }
 #undef CKD
     s->cav_host.resize(cfg->batch);
     {
@@ -799,6 +843,10 @@ int lbm_init_equilibrium(lbm_handle_t s) {
         b.rho = (char*)a.rho + (size_t)off * s->pitch * s->esz;
         b.ux = (char*)a.ux + (size_t)off * s->pitch * s->esz;
         b.uy = (char*)a.uy + (size_t)off * s->pitch * s->esz;
+        if (a.pi_eq) {
+            b.pi_eq = (char*)a.pi_eq + (size_t)off * s->pitch * s->esz;
+            b.rho_prev = (char*)a.rho_prev + (size_t)off * s->pitch * s->esz;
+        }
         grid.y = n;
         if (s->cfg.dtype == LBM_F64) lbm_init_eq<double><<<grid, 256>>>(b);
         else lbm_init_eq<float><<<grid, 256>>>(b);
@@ -873,6 +921,12 @@ int lbm_upload_f(lbm_handle_t s, const void* f, int on_device, void* stream) {
         lbm_fill<float><<<1024, 256, 0, st>>>((float*)s->uy, n, 0.0f);
     }
     s->launches += 4;
+    if (s->cfg.turb) {
+        dim3 g((s->cfg.nx + 255) / 256, s->nyl, s->cfg.batch);
+        if (s->esz == 8) lbm_seed_turb<double><<<g, 256, 0, st>>>(a);
+        else lbm_seed_turb<float><<<g, 256, 0, st>>>(a);
+        s->launches++;
+    }
     CK(cudaGetLastError());
     s->cur = 0; s->pre = true; s->steps = 0;
     return LBM_OK;

@@ -34,6 +34,8 @@ struct StepArgs {
     void* uy;
     void* rho_lid;             // [batch][pitch]
     void* carry;               // [batch][4]
+    void* pi_eq;               // [batch][nyl][pitch]  sum_k cx cy feq_k of the previous step (Smagorinsky only)
+    void* rho_prev;            // [batch][nyl][pitch]  rho of the previous step            (Smagorinsky only)
     const CavityParams* cav;   // [batch]
     int nx, ny, y0, nyl, pitch;
     long long plane, cavity;   // elements
@@ -168,6 +170,59 @@ __device__ __forceinline__ void collide_trt(T f[9], T rho, T ux, T uy, T omegap,
     }
 }
 
+// ---- fp32 accuracy: deviation form of SRT / TRT -----------------------------------------------------------------
+// In fp32 the reference-order expression f - omega (f - feq) injects ~ulp(feq) = 3e-8 of noise per step into the
+// conserved density (measured: 3e-6 in rho, 1e-5 of uLB in u after 150 steps at tau = 0.54, ten times the MRT path,
+// whose correction form never rounds at the magnitude of f).  The same collision evaluated on the deviations
+// g_k = f_k - t_k (exact by Sterbenz) and feq_k - t_k = t_k (drho + rho (3cu + 4.5cu^2 - 1.5u^2)) only rounds at the
+// magnitude of the deviations.  Used for T = float only; fp64 keeps the reference's operation order.
+// (The reference's own fp32 kernels evaluate these expressions with double literals, i.e. in mixed precision.)
+template <typename T>
+__device__ __forceinline__ T drho_of(const T f[9], bool lid) {
+    const T g0 = f[0] - w_rest<T>(), g1 = f[1] - w_axis<T>(), g2 = f[2] - w_axis<T>(), g3 = f[3] - w_axis<T>(),
+            g4 = f[4] - w_axis<T>(), g5 = f[5] - w_diag<T>(), g6 = f[6] - w_diag<T>(), g7 = f[7] - w_diag<T>(),
+            g8 = f[8] - w_diag<T>();
+    if (lid) return g0 + g1 + g3 + (T)2 * (g2 + g5 + g6);        // lid formula: the weights sum to exactly 1
+    return g0 + g1 + g2 + g3 + g4 + g5 + g6 + g7 + g8;
+}
+template <typename T>
+__device__ __forceinline__ void feq_dev_all(T drho, T rho, T ux, T uy, T fd[9]) {
+    const T usqr = ux * ux + uy * uy;
+    const T cu[9] = {(T)0, ux, uy, -ux, -uy, ux + uy, -ux + uy, -ux - uy, ux - uy};
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const T tk = k == 0 ? w_rest<T>() : (k < 5 ? w_axis<T>() : w_diag<T>());
+        fd[k] = tk * (drho + rho * ((T)3.0 * cu[k] + (T)4.5 * cu[k] * cu[k] - (T)1.5 * usqr));
+    }
+}
+template <typename T>
+__device__ __forceinline__ T weight_of(int k) { return k == 0 ? w_rest<T>() : (k < 5 ? w_axis<T>() : w_diag<T>()); }
+
+template <typename T>
+__device__ __forceinline__ void collide_srt_dev(T f[9], T drho, T rho, T ux, T uy, T omega) {
+    T fd[9];
+    feq_dev_all<T>(drho, rho, ux, uy, fd);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f[k] = f[k] - omega * ((f[k] - weight_of<T>(k)) - fd[k]);
+}
+template <typename T>
+__device__ __forceinline__ void collide_trt_dev(T f[9], T drho, T rho, T ux, T uy, T omegap, T omegam) {
+    T fd[9];
+    feq_dev_all<T>(drho, rho, ux, uy, fd);
+    const T h = (T)0.5;
+    f[0] = f[0] - omegap * ((f[0] - w_rest<T>()) - fd[0]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int a = (i < 2) ? i + 1 : i + 3;
+        const int o = a + 2;
+        const T ga = f[a] - weight_of<T>(a), go = f[o] - weight_of<T>(o);
+        const T sp = h * ((ga + go) - (fd[a] + fd[o]));      // f+ - feq+
+        const T sm = h * ((ga - go) - (fd[a] - fd[o]));      // f- - feq-   (opposite sign for o)
+        f[a] = f[a] - omegap * sp - omegam * sm;
+        f[o] = f[o] - omegap * sp + omegam * sm;
+    }
+}
+
 // MRT in the Gram-Schmidt basis of MRT_GPU.py:593-612 with the reference's (non-standard) equilibrium moments
 // (:636-644: momentum not velocity, +9 jx^2 jy^2, cubic heat-flux terms) and rates s = [0,s_e,s_eps,0,s_q,0,s_q,s_nu,s_nu].
 // Evaluated as f* = f - Minv * S * (m - m_eq) with M and Minv hand-factored (entries 0,+-1,+-2,+-4 / 1/4..1/36):
@@ -218,15 +273,27 @@ __device__ __forceinline__ void collide_mrt(T f[9], T rho, T s_e, T s_eps, T s_q
     f[8] = f[8] + (dg_p - qd);
 }
 
+// Smagorinsky closure of MRT_GPU.py:570-589: effective relaxation rate from the non-equilibrium momentum flux
+// Q = sum_k cx cy (f_k - feq_k^prev), with feq and rho of the PREVIOUS step (the reference reads feq_g / rho_g before
+// overwriting them) and Cs2 hard-set to 0.025 (:578; the Van-Driest lines above it are dead code).
+template <typename T>
+__device__ __forceinline__ T smagorinsky_omega(const T f[9], T pi_prev, T rho_prev, T omega) {
+    const T product1 = f[5] - f[6] + f[7] - f[8];
+    const T Qmf = product1 - pi_prev;
+    const T tau0 = (T)1.0 / omega;
+    const T tau = (T)0.5 * (tau0 + sqrt(tau0 * tau0 + ((T)(18 * 1.4142 * 0.025) * fabs(Qmf)) / rho_prev));
+    return (T)1.0 / tau;
+}
+
 // Everything after the gather for one node: overrides, optional macro output values, collision in place.
-// Returns rho (lid-overridden) and the output velocity through the references.
-template <typename T, int COLL, bool NEED_U>
+// Returns rho (lid-overridden) and the output velocity through the references; with TURB also sum_k cx cy feq_k.
+template <typename T, int COLL, bool NEED_U, bool TURB = false>
 __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left, bool right, bool lid, bool bot,
-                                            T& rho_out, T& ux_out, T& uy_out) {
+                                            T& rho_out, T& ux_out, T& uy_out, T omega_nu = (T)0, T* pi_out = nullptr) {
     T rho, jx, jy;
     moments_ref<T>(f, rho, jx, jy);
     T ux = (T)0, uy = (T)0;
-    if (NEED_U || COLL != COLL_MRT) {
+    if (NEED_U || TURB || COLL != COLL_MRT) {
         ux = jx / rho;
         uy = jy / rho;
     }
@@ -237,9 +304,23 @@ __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left
         uy = (T)0;
     }
     rho_out = rho; ux_out = ux; uy_out = uy;
-    if (COLL == COLL_SRT) collide_srt<T>(f, rho, ux, uy, r.omega);
-    else if (COLL == COLL_TRT) collide_trt<T>(f, rho, ux, uy, r.omega, r.omegam);
-    else collide_mrt<T>(f, rho, r.s_e, r.s_eps, r.s_q, r.omega);
+    const T om = TURB ? omega_nu : r.omega;
+    if (TURB) {
+        const T usqr = ux * ux + uy * uy;
+        const T fe5 = feq_one(rho, w_diag<T>(), ux + uy, usqr), fe6 = feq_one(rho, w_diag<T>(), -ux + uy, usqr);
+        const T fe7 = feq_one(rho, w_diag<T>(), -ux - uy, usqr), fe8 = feq_one(rho, w_diag<T>(), ux - uy, usqr);
+        *pi_out = fe5 - fe6 + fe7 - fe8;
+    }
+    if (COLL == COLL_MRT) {
+        collide_mrt<T>(f, rho, r.s_e, r.s_eps, r.s_q, om);
+    } else if (sizeof(T) == 4) {
+        const T drho = drho_of<T>(f, lid);
+        if (COLL == COLL_SRT) collide_srt_dev<T>(f, drho, rho, ux, uy, om);
+        else collide_trt_dev<T>(f, drho, rho, ux, uy, om, r.omegam);
+    } else {
+        if (COLL == COLL_SRT) collide_srt<T>(f, rho, ux, uy, om);
+        else collide_trt<T>(f, rho, ux, uy, om, r.omegam);
+    }
 }
 
 }  // namespace lbm
