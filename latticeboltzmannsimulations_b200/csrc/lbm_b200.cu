@@ -47,8 +47,9 @@ static int fail(int code, const std::string& msg) {
 template <typename T, int COLL, bool GATHER, bool MACROS, int MODE, bool TURB = false>
 __global__ void __launch_bounds__(256) lbm_step_ldg(const StepArgs a) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= a.nx) return;
-    const int yl = a.row_begin + blockIdx.y * a.row_stride;
+    const int lr = blockIdx.y * blockDim.y + threadIdx.y;          // launch row
+    if (x >= a.nx || lr >= a.row_count) return;
+    const int yl = a.row_begin + lr * a.row_stride;
     const int b = blockIdx.z;
     const int y = a.y0 + yl;
     const bool left = (x == 0), right = (x == a.nx - 1), lid = (y == 0), bot = (y == a.ny - 1);
@@ -156,9 +157,11 @@ __device__ __forceinline__ void gstore(T* p, const T in[V]) {
 
 template <typename T, int COLL, bool MACROS, int V>
 __global__ void __launch_bounds__(256) lbm_step_vec(const StepArgs a) {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;                                  // blockDim.x is a multiple of 32: a warp is one row
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * V;          // first node of this thread
-    const int yl = a.row_begin + blockIdx.y * a.row_stride;
+    const int lr = blockIdx.y * blockDim.y + threadIdx.y;               // launch row (warp-uniform)
+    if (lr >= a.row_count) return;
+    const int yl = a.row_begin + lr * a.row_stride;
     const int b = blockIdx.z;
     const int y = a.y0 + yl;
     const bool lid = (y == 0), bot = (y == a.ny - 1);
@@ -531,19 +534,21 @@ static cudaError_t launch_tma_coll(lbm_solver* s, const CUtensorMap* tm, const S
 }
 
 // ---- kernel dispatch ----------------------------------------------------------------------------------------
+static thread_local dim3 g_block(256, 1, 1);      // block shape of the scalar family for the current launch
+
 template <typename T, int COLL, bool GATHER, bool MACROS, int MODE>
 static void launch_ldg(const StepArgs& a, dim3 grid, cudaStream_t st) {
-    lbm_step_ldg<T, COLL, GATHER, MACROS, MODE><<<grid, 256, 0, st>>>(a);
+    lbm_step_ldg<T, COLL, GATHER, MACROS, MODE><<<grid, g_block, 0, st>>>(a);
 }
 
 template <typename T, int COLL, bool TURB>
 static void dispatch_step(const StepArgs& a, dim3 grid, cudaStream_t st, bool gather, bool macros) {
     if (gather) {
-        if (macros) lbm_step_ldg<T, COLL, true, true, MODE_STEP, TURB><<<grid, 256, 0, st>>>(a);
-        else lbm_step_ldg<T, COLL, true, false, MODE_STEP, TURB><<<grid, 256, 0, st>>>(a);
+        if (macros) lbm_step_ldg<T, COLL, true, true, MODE_STEP, TURB><<<grid, g_block, 0, st>>>(a);
+        else lbm_step_ldg<T, COLL, true, false, MODE_STEP, TURB><<<grid, g_block, 0, st>>>(a);
     } else {
-        if (macros) lbm_step_ldg<T, COLL, false, true, MODE_STEP, TURB><<<grid, 256, 0, st>>>(a);
-        else lbm_step_ldg<T, COLL, false, false, MODE_STEP, TURB><<<grid, 256, 0, st>>>(a);
+        if (macros) lbm_step_ldg<T, COLL, false, true, MODE_STEP, TURB><<<grid, g_block, 0, st>>>(a);
+        else lbm_step_ldg<T, COLL, false, false, MODE_STEP, TURB><<<grid, g_block, 0, st>>>(a);
     }
 }
 
@@ -569,12 +574,28 @@ static void dispatch_coll(int coll, const StepArgs& a, dim3 grid, cudaStream_t s
     }
 }
 
+// Block shape for `threads_x` threads along a row: blockDim.x from {256,...,32} with the least idle lanes (ties go
+// to the wider block), blockDim.y rows so that a block has up to 256 threads.
+static void block_shape(int threads_x, int rows, dim3* block, dim3* grid, int batch) {
+    int best = 256, waste = 1 << 30;
+    for (int bx = 256; bx >= 32; bx -= 32) {
+        const int w = (threads_x + bx - 1) / bx * bx - threads_x;
+        if (w < waste) { waste = w; best = bx; }
+    }
+    int by = 256 / best;
+    if (by > rows) by = rows;
+    if (by < 1) by = 1;
+    *block = dim3(best, by, 1);
+    *grid = dim3((threads_x + best - 1) / best, (rows + by - 1) / by, batch);
+}
+
 // ---- vector ldg dispatch (hot path) ---------------------------------------------------------------------------
 template <typename T, int COLL, int V>
 static void launch_vec_flags(const StepArgs& a, int nx, int rows, int batch, cudaStream_t st, bool macros) {
-    dim3 grid((nx + 256 * V - 1) / (256 * V), rows, batch);
-    if (macros) lbm_step_vec<T, COLL, true, V><<<grid, 256, 0, st>>>(a);
-    else lbm_step_vec<T, COLL, false, V><<<grid, 256, 0, st>>>(a);
+    dim3 block, grid;
+    block_shape((nx + V - 1) / V, rows, &block, &grid, batch);
+    if (macros) lbm_step_vec<T, COLL, true, V><<<grid, block, 0, st>>>(a);
+    else lbm_step_vec<T, COLL, false, V><<<grid, block, 0, st>>>(a);
 }
 template <typename T, int V>
 static void launch_vec_coll(int coll, const StepArgs& a, int nx, int rows, int batch, cudaStream_t st, bool macros) {
@@ -602,7 +623,9 @@ static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin,
         if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("tma launch: ") + cudaGetErrorString(e));
         return LBM_OK;
     }
-    dim3 grid((s->cfg.nx + 255) / 256, row_count, s->cfg.batch);
+    a.row_count = row_count;
+    dim3 grid;
+    block_shape(s->cfg.nx, row_count, &g_block, &grid, s->cfg.batch);
     if (grid.y > 65535u || grid.z > 65535u) {
         // split over rows in chunks the grid can express
         const int chunk = 65535;

@@ -40,7 +40,8 @@ struct StepArgs {
     int nx, ny, y0, nyl, pitch;
     long long plane, cavity;   // elements
     long long mplane;          // macro plane = nyl * pitch elements
-    int row_begin, row_stride; // local row of blockIdx.y == 0 and distance between consecutive blockIdx.y
+    int row_begin, row_stride; // local row of launch row 0 and distance between consecutive launch rows
+    int row_count;             // launch rows (blockIdx.y * blockDim.y + threadIdx.y < row_count)
 };
 
 template <typename T>
@@ -294,8 +295,14 @@ __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left
     moments_ref<T>(f, rho, jx, jy);
     T ux = (T)0, uy = (T)0;
     if (NEED_U || TURB || COLL != COLL_MRT) {
-        ux = jx / rho;
-        uy = jy / rho;
+        if (sizeof(T) == 4) {            // fp32: one reciprocal + two multiplies (the fp64 path keeps true divisions)
+            const T inv = (T)1 / rho;
+            ux = jx * inv;
+            uy = jy * inv;
+        } else {
+            ux = jx / rho;
+            uy = jy / rho;
+        }
     }
     if (left || right || bot) { ux = (T)0; uy = (T)0; }
     if (lid) {
