@@ -119,6 +119,14 @@ int lbm_get_macros_current(lbm_handle_t h, void* rho, void* u, int on_device, vo
 int lbm_equilibrium(int dtype, int64_t n, const void* rho, const void* ux, const void* uy, void* feq,
                     int on_device, void* stream);
 
+/* Per-cavity np.mean(u) over both components of the stored (lagged) velocity field -- the quantity of the
+ * convergence test `abs(np.mean(u) - np.mean(u_past)) / uLB < 1e-7` in MRT_GPU_datagen.py:729 (MRT_GPU.py:883),
+ * reduced on the device.  mean_out: [batch] doubles on the host. */
+int lbm_mean_u(lbm_handle_t h, double* mean_out, void* stream);
+/* Freeze cavities of a batch (active[b] == 0): the `break` of MRT_GPU_datagen.py:731-733 per cavity.  Frozen
+ * cavities keep their populations and macros and no longer cost bandwidth; they cannot be re-activated. */
+int lbm_set_active(lbm_handle_t h, const int32_t* active, void* stream);
+
 int lbm_sync(lbm_handle_t h);
 /* Steps completed, and number of kernels this handle has launched (for the bench's gpu_launches). */
 int lbm_get_counters(lbm_handle_t h, int64_t* steps_done, int64_t* kernel_launches);

@@ -39,31 +39,68 @@ def run_cavity(nx: int, ny: int, Re: float, uLB: float = 0.08, steps: int = 1000
 
 def datagen(Re_list: Sequence[float], nx: int = 384, ny: int = 384, uLB: float = 0.08, steps: int = 10000,
             collision: str = "MRT", dtype="float32", turb: bool = False, device: Optional[int] = None,
-            engine: str = "auto", chunk: Optional[int] = None):
-    """Batched Reynolds sweep of ``MRT_GPU_datagen.py``: every cavity of ``Re_list`` advanced ``steps`` steps.
+            engine: str = "auto", chunk: Optional[int] = None, converge: bool = False, Pinterval: int = 10000,
+            maxIt: int = 3000000, tol: float = 1e-7, hits: int = 6, return_steps: bool = False):
+    """Batched Reynolds sweep of ``MRT_GPU_datagen.py``: one cavity per entry of ``Re_list``.
 
     Returns ``(f_final[N,9,nx,ny], u_final[N,2,nx,ny], feq_initial[9,nx,ny], Re_range[N])`` in the dtype / ``[x,y]``
     indexing of the files the reference saves (``:899-902``).  Cavities are independent (no communication); the
     multi-GPU driver (``distributed.datagen_sharded``) gives rank r the cavities ``r::world``.
+
+    ``converge=False``: every cavity advances exactly ``steps`` steps (fixed work, used for timing).
+    ``converge=True``: the reference's stopping rule (``:716-737``), evaluated per cavity on the device: at every
+    iteration ``It`` with ``It % Pinterval == 0`` the mean of the stored velocity field is compared with the one of
+    the previous check, ``abs(mean(u) - mean(u_past)) / uLB < tol`` increments a counter (never reset, as in the
+    reference) and the cavity stops when it exceeds ``hits - 1`` or at ``maxIt``; its ``fin`` / ``u`` at that
+    moment are what is returned.  Stopped cavities are frozen on the device and cost no further bandwidth.
     """
     Re_arr = np.asarray(list(Re_list), dtype=np.float64)
     n = len(Re_arr)
     _, npdt = {"float32": (0, np.float32), "float64": (1, np.float64)}[np.dtype(dtype).name]
     f_final = np.empty((n, 9, nx, ny), dtype=npdt)
     u_final = np.empty((n, 2, nx, ny), dtype=npdt)
+    steps_done = np.zeros(n, dtype=np.int64)
     feq_initial = None
     chunk = n if chunk is None else max(1, int(chunk))
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)
-        with CavitySolver(nx, ny, hi - lo, dtype, collision, turb, device=device, engine=engine) as s:
+        nb = hi - lo
+        with CavitySolver(nx, ny, nb, dtype, collision, turb, device=device, engine=engine) as s:
             s.set_reynolds(Re_arr[lo:hi], uLB)
             s.init_equilibrium()
             if feq_initial is None:
                 f_init = s.download_f()
-                feq_initial = np.array(f_init if hi - lo == 1 else f_init[0])
-            s.step(int(steps), write_macros=True)
+                feq_initial = np.array(f_init if nb == 1 else f_init[0])
+            if not converge:
+                s.step(int(steps), write_macros=True)
+                steps_done[lo:hi] = int(steps)
+            else:
+                count = np.zeros(nb, dtype=np.int64)
+                past = np.zeros(nb)                       # u_past starts as zeros (MRT_GPU_datagen.py:223)
+                active = np.ones(nb, dtype=np.int32)
+                it = 0
+                while it < maxIt and active.any():
+                    s.step(1, write_macros=True)          # iteration `it`, followed by the check of :724-737
+                    mean = s.mean_u()
+                    hit = (np.abs(mean - past) / uLB < tol) & (active == 1)
+                    count += hit
+                    past = np.where(active == 1, mean, past)
+                    done = (count > hits - 1) & (active == 1)
+                    steps_done[lo:hi][active == 1] = it + 1
+                    if done.any():
+                        active[done] = 0
+                        s.set_active(active)
+                    if not active.any():
+                        break
+                    nxt = min(Pinterval - 1, maxIt - it - 1)
+                    if nxt > 0:
+                        s.step(nxt, write_macros=False)
+                        steps_done[lo:hi][active == 1] = it + 1 + nxt
+                    it += Pinterval
             _, u = s.macros()
             f = s.download_f()
-            f_final[lo:hi] = f.reshape(hi - lo, 9, nx, ny)
-            u_final[lo:hi] = u.reshape(hi - lo, 2, nx, ny)
+            f_final[lo:hi] = f.reshape(nb, 9, nx, ny)
+            u_final[lo:hi] = u.reshape(nb, 2, nx, ny)
+    if return_steps:
+        return f_final, u_final, feq_initial, Re_arr, steps_done
     return f_final, u_final, feq_initial, Re_arr

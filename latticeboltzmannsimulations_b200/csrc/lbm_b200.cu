@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) lbm_step_ldg(const StepArgs a) {
     if (x >= a.nx || lr >= a.row_count) return;
     const int yl = a.row_begin + lr * a.row_stride;
     const int b = blockIdx.z;
+    if (MODE == MODE_STEP && a.active && !a.active[b]) return;       // frozen (converged) cavity
     const int y = a.y0 + yl;
     const bool left = (x == 0), right = (x == a.nx - 1), lid = (y == 0), bot = (y == a.ny - 1);
     const T* __restrict__ src = static_cast<const T*>(a.src) + (long long)b * a.cavity;
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(256) lbm_step_vec(const StepArgs a) {
     if (lr >= a.row_count) return;
     const int yl = a.row_begin + lr * a.row_stride;
     const int b = blockIdx.z;
+    if (a.active && !a.active[b]) return;                               // frozen (converged) cavity
     const int y = a.y0 + yl;
     const bool lid = (y == 0), bot = (y == a.ny - 1);
     const bool active = x < a.nx;                                       // whole warps may be partially outside
@@ -375,6 +377,31 @@ __global__ void lbm_equ_kernel(const T* __restrict__ rho, const T* __restrict__ 
     }
 }
 
+// np.mean(u) of MRT_GPU_datagen.py:729 per cavity: sum of both stored velocity components over the valid nodes,
+// accumulated in fp64 (block tree + one atomicAdd per block).
+template <typename T>
+__global__ void lbm_sum_u(const T* __restrict__ ux, const T* __restrict__ uy, double* __restrict__ out, int nx, int nyl,
+                          int pitch, long long mplane) {
+    const int b = blockIdx.y;
+    const long long n = (long long)nyl * pitch;
+    const T* px = ux + (long long)b * mplane;
+    const T* py = uy + (long long)b * mplane;
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % pitch);
+        if (x < nx) acc += (double)px[i] + (double)py[i];
+    }
+    __shared__ double sh[32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (threadIdx.x == 0) atomicAdd(&out[b], acc);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // solver object
 // ------------------------------------------------------------------------------------------------------------
@@ -396,6 +423,9 @@ struct lbm_solver {
     void* carry = nullptr;
     void* pi_eq = nullptr;     // Smagorinsky state (turb = 1 only)
     void* rho_prev = nullptr;
+    int* active = nullptr;     // device copy of the per-cavity active flags (NULL until lbm_set_active is used)
+    std::vector<int> active_host;
+    double* usum = nullptr;    // [batch] accumulator of lbm_mean_u
     CavityParams* cav = nullptr;
     std::vector<CavityParams> cav_host;
     bool cav_dirty = true;
@@ -419,6 +449,15 @@ struct lbm_solver {
     int use_graph = 1;
 };
 
+// A fresh state (init / upload) un-freezes every cavity; graphs captured with the old flag pointer are dropped.
+static void reset_active(lbm_solver* s) {
+    if (!s->active) return;
+    cudaFree(s->active);
+    s->active = nullptr;
+    for (int i = 0; i < 2; ++i)
+        if (s->graph[i]) { cudaGraphExecDestroy(s->graph[i]); s->graph[i] = nullptr; }
+}
+
 static int set_device(lbm_solver* s) {
     CK(cudaSetDevice(s->device));
     return LBM_OK;
@@ -430,6 +469,7 @@ static StepArgs make_args(lbm_solver* s, const void* src, void* dst) {
     a.rho = s->rho; a.ux = s->ux; a.uy = s->uy;
     a.rho_lid = s->rho_lid; a.carry = s->carry; a.cav = s->cav;
     a.pi_eq = s->pi_eq; a.rho_prev = s->rho_prev;
+    a.active = s->active;
     a.nx = s->cfg.nx; a.ny = s->cfg.ny; a.y0 = s->cfg.y0; a.nyl = s->nyl; a.pitch = s->pitch;
     a.plane = s->plane; a.cavity = s->cavity; a.mplane = s->mplane;
     a.row_begin = 0; a.row_stride = 1;
@@ -612,7 +652,7 @@ static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin,
     if (row_count <= 0) return LBM_OK;
     StepArgs a = make_args(s, src, dst);
     a.row_begin = row_begin; a.row_stride = row_stride;
-    if (s->engine == LBM_ENGINE_TMA && s->tmap_ok && !s->cfg.turb && mode == MODE_STEP && gather && !macros && row_stride == 1 &&
+    if (s->engine == LBM_ENGINE_TMA && s->tmap_ok && !s->cfg.turb && !s->active && mode == MODE_STEP && gather && !macros && row_stride == 1 &&
         (src == s->f[0] || src == s->f[1])) {
         TileSched ts{};
         ts.row_begin = row_begin; ts.row_count = row_count; ts.rows_per_plane = s->nyl + 2;
@@ -723,6 +763,7 @@ int lbm_destroy(lbm_handle_t s) {
     cudaFree(s->rho); cudaFree(s->ux); cudaFree(s->uy);
     cudaFree(s->rho_lid); cudaFree(s->carry); cudaFree(s->cav);
     cudaFree(s->pi_eq); cudaFree(s->rho_prev);
+    cudaFree(s->active); cudaFree(s->usum);
     cudaFree(s->staging); cudaFree(s->scratch);
     for (int i = 0; i < 2; ++i) if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
     if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
@@ -877,6 +918,7 @@ int lbm_init_equilibrium(lbm_handle_t s) {
     }
     CK(cudaGetLastError());
     s->cur = 0; s->pre = true; s->steps = 0;
+    reset_active(s);
     return LBM_OK;
 }
 
@@ -952,6 +994,7 @@ int lbm_upload_f(lbm_handle_t s, const void* f, int on_device, void* stream) {
     }
     CK(cudaGetLastError());
     s->cur = 0; s->pre = true; s->steps = 0;
+    reset_active(s);
     return LBM_OK;
 }
 
@@ -1126,6 +1169,55 @@ int lbm_equilibrium(int dtype, int64_t n, const void* rho, const void* ux, const
     }
     if (d) cudaFree(d);
     if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("lbm_equilibrium: ") + cudaGetErrorString(e));
+    return LBM_OK;
+}
+
+int lbm_mean_u(lbm_handle_t s, double* mean_out, void* stream) {
+    if (!s || !mean_out) return fail(LBM_EINVAL, "NULL argument");
+    int rc = set_device(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = s->cfg.batch;
+    if (!s->usum) CK(cudaMalloc(&s->usum, sizeof(double) * nb));
+    CK(cudaMemsetAsync(s->usum, 0, sizeof(double) * nb, st));
+    dim3 grid(148 * 2, nb);
+    if (s->esz == 8) lbm_sum_u<double><<<grid, 256, 0, st>>>((const double*)s->ux, (const double*)s->uy, s->usum, s->cfg.nx, s->nyl, s->pitch, s->mplane);
+    else lbm_sum_u<float><<<grid, 256, 0, st>>>((const float*)s->ux, (const float*)s->uy, s->usum, s->cfg.nx, s->nyl, s->pitch, s->mplane);
+    s->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(mean_out, s->usum, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const double denom = 2.0 * (double)s->cfg.nx * (double)s->nyl;
+    for (int b = 0; b < nb; ++b) mean_out[b] /= denom;
+    return LBM_OK;
+}
+
+int lbm_set_active(lbm_handle_t s, const int32_t* active, void* stream) {
+    if (!s || !active) return fail(LBM_EINVAL, "NULL argument");
+    int rc = set_device(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = s->cfg.batch;
+    if (!s->active) {
+        CK(cudaMalloc(&s->active, sizeof(int) * nb));
+        s->active_host.assign(nb, 1);
+        for (int i = 0; i < 2; ++i)
+            if (s->graph[i]) { cudaGraphExecDestroy(s->graph[i]); s->graph[i] = nullptr; }   // kernel args change
+    }
+    const size_t cav_bytes = (size_t)s->cavity * s->esz;
+    for (int b = 0; b < nb; ++b) {
+        const int now = active[b] ? 1 : 0;
+        if (s->active_host[b] && !now) {
+            // freeze: both A/B buffers must hold the cavity's current populations, whatever the parity later on
+            CK(cudaMemcpyAsync((char*)s->f[s->cur ^ 1] + b * cav_bytes, (char*)s->f[s->cur] + b * cav_bytes, cav_bytes,
+                               cudaMemcpyDeviceToDevice, st));
+        } else if (!s->active_host[b] && now) {
+            return fail(LBM_ESTATE, "a frozen cavity cannot be re-activated");
+        }
+        s->active_host[b] = now;
+    }
+    CK(cudaMemcpyAsync(s->active, s->active_host.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
     return LBM_OK;
 }
 

@@ -37,6 +37,7 @@ struct StepArgs {
     void* pi_eq;               // [batch][nyl][pitch]  sum_k cx cy feq_k of the previous step (Smagorinsky only)
     void* rho_prev;            // [batch][nyl][pitch]  rho of the previous step            (Smagorinsky only)
     const CavityParams* cav;   // [batch]
+    const int* active;         // [batch] or NULL: cavities with active[b] == 0 are frozen (skipped by step launches)
     int nx, ny, y0, nyl, pitch;
     long long plane, cavity;   // elements
     long long mplane;          // macro plane = nyl * pitch elements

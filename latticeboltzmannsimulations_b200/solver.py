@@ -171,6 +171,19 @@ class CavitySolver:
         _capi.check(fn(self._h, rp, up, d1, C.c_void_p(stream)))
         return rho_out, u_out
 
+    def mean_u(self, stream: int = 0) -> np.ndarray:
+        """Per-cavity ``np.mean(u)`` of the stored velocity field, reduced on the device (MRT_GPU_datagen.py:729)."""
+        out = (C.c_double * self.batch)()
+        _capi.check(self._lib.lbm_mean_u(self._h, out, C.c_void_p(stream)))
+        return np.array(out[:], dtype=np.float64)
+
+    def set_active(self, active, stream: int = 0) -> None:
+        """Freeze the cavities whose flag is 0 (per-cavity ``break`` of MRT_GPU_datagen.py:731-733)."""
+        flags = np.ascontiguousarray(np.asarray(active, dtype=np.int32))
+        if flags.shape != (self.batch,):
+            raise ValueError("need one flag per cavity")
+        _capi.check(self._lib.lbm_set_active(self._h, flags.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(stream)))
+
     def sync(self) -> None:
         _capi.check(self._lib.lbm_sync(self._h))
 

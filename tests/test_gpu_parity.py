@@ -239,3 +239,50 @@ def test_full_size_properties_4096(dtype):
     want = O.run(p, 50, form="pull")[2]
     tol = TOL[dtype]
     assert np.abs(f[:, :100, :100] - want[:, :100, :100]).max() <= tol
+
+
+def test_mean_u_and_freeze():
+    """Device reduction == np.mean of the downloaded field; a frozen cavity stops exactly where it was frozen
+    while the others continue (each still equal to its standalone run, bit for bit)."""
+    import latticeboltzmannsimulations_b200 as L
+    nx, ny, Re = 56, 40, [100.0, 400.0, 1000.0]
+    with L.CavitySolver(nx, ny, 3, "float64", "MRT") as s:
+        s.set_reynolds(Re)
+        s.init_equilibrium()
+        s.step(60, write_macros=True)
+        rho, u = s.macros()
+        m = s.mean_u()
+        assert np.abs(m - u.reshape(3, -1).mean(axis=1)).max() <= 1e-15
+        s.set_active([1, 0, 1])
+        s.step(41, write_macros=True)       # odd count: the frozen cavity must survive the A/B parity flip
+        f = s.download_f()
+        rho2, u2 = s.macros()
+    for b, steps in ((0, 101), (1, 60), (2, 101)):
+        r0, u0, f0 = L.run_cavity(nx, ny, Re[b], steps=steps, return_f=True)
+        assert np.array_equal(f[b], f0) and np.array_equal(u2[b], u0) and np.array_equal(rho2[b], r0), b
+
+
+def test_datagen_convergence_rule_matches_reference_loop():
+    """datagen(converge=True) against a literal restatement of the loop of MRT_GPU_datagen.py:716-737 driven by the
+    oracle (np.mean of the lagged u every Pinterval iterations, cumulative hit counter, break at count > 5)."""
+    import latticeboltzmannsimulations_b200 as L
+    nx = ny = 24
+    Re_list, P, tol, maxIt = [20.0, 60.0], 200, 1e-5, 20000
+    f_final, u_final, feq0, Re_out, steps = L.datagen(Re_list, nx, ny, collision="MRT", dtype="float64", converge=True,
+                                                      Pinterval=P, tol=tol, maxIt=maxIt, return_steps=True)
+    for b, Re in enumerate(Re_list):
+        p = O.Params(nx, ny, Re=Re, collision="MRT")
+        ps = O.PullState.from_fin(O.init_fields(nx, ny, 0.08)[2], p)
+        u_past = np.zeros((2, nx, ny)); count = 0; fin = u = None
+        for It in range(maxIt):
+            O.step_C_pull(ps, p)
+            if It % P == 0:
+                u = ps.u.copy(); fin = O.fin_from_pull(ps, p)
+                if abs(np.mean(u) - np.mean(u_past)) / 0.08 < tol:
+                    count += 1
+                    if count > 5:
+                        break
+                u_past = u.copy()
+        assert steps[b] == It + 1, (steps[b], It + 1)
+        assert 6 * P < It + 1 < maxIt                      # really stopped by the rule, after some transient
+        assert np.abs(f_final[b] - fin).max() <= 1e-12 and np.abs(u_final[b] - u).max() / 0.08 <= 1e-12
