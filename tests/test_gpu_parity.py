@@ -286,3 +286,47 @@ def test_datagen_convergence_rule_matches_reference_loop():
         assert steps[b] == It + 1, (steps[b], It + 1)
         assert 6 * P < It + 1 < maxIt                      # really stopped by the rule, after some transient
         assert np.abs(f_final[b] - fin).max() <= 1e-12 and np.abs(u_final[b] - u).max() / 0.08 <= 1e-12
+
+
+def test_device_resident_io_with_torch_tensors():
+    """Zero-copy path of the C ABI (on_device = 1): torch CUDA tensors in the reference layout go in and come out
+    without touching the host, on a non-default stream, and give the same bits as the host-array path."""
+    import torch
+    import latticeboltzmannsimulations_b200 as L
+    nx, ny, n = 70, 52, 37
+    f0 = O.random_state(nx, ny, seed=21)
+    want = L.run_cavity(nx, ny, 400, steps=n, f0=f0, return_f=True)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        f_dev = torch.from_numpy(f0).cuda(non_blocking=False)
+        with L.CavitySolver(nx, ny, 1, "float64", "MRT") as s:
+            s.set_reynolds(400)
+            s.upload_f(f_dev, stream=st.cuda_stream)
+            s.step(n, write_macros=True, stream=st.cuda_stream)
+            rho_d = torch.empty((nx, ny), dtype=torch.float64, device="cuda")
+            u_d = torch.empty((2, nx, ny), dtype=torch.float64, device="cuda")
+            f_d = torch.empty((9, nx, ny), dtype=torch.float64, device="cuda")
+            s.macros(rho_out=rho_d, u_out=u_d, stream=st.cuda_stream)
+            s.download_f(out=f_d, stream=st.cuda_stream)
+            st.synchronize()
+            with pytest.raises(ValueError):
+                s.upload_f(f_dev.float())                     # wrong dtype is rejected, never converted silently
+    assert np.array_equal(rho_d.cpu().numpy(), want[0]) and np.array_equal(u_d.cpu().numpy(), want[1])
+    assert np.array_equal(f_d.cpu().numpy(), want[2])
+
+
+def test_error_paths():
+    import latticeboltzmannsimulations_b200 as L
+    with pytest.raises(L.LBMError, match="nx and ny"):
+        L.CavitySolver(2, 10)
+    with pytest.raises(L.LBMError, match="y-strip"):
+        L.CavitySolver(32, 32, y0=20, ny_local=20)
+    with L.CavitySolver(32, 32, y0=0, ny_local=16) as s:
+        s.set_reynolds(100); s.init_equilibrium()
+        with pytest.raises(L.LBMError, match="halo exchange"):
+            s.step(2)
+    with L.CavitySolver(32, 32) as s:
+        with pytest.raises(L.LBMError, match="omega_nu"):
+            s.set_rates(0.08, 2.5)
+        with pytest.raises(ValueError, match="expected shape"):
+            s.upload_f(np.zeros((9, 32, 31)))

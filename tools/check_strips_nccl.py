@@ -37,6 +37,34 @@ if rank == 0:
         same = np.array_equal(f, f_final[b]) and np.array_equal(u, u_final[b])
         print("sweep cavity", b, "bitwise equal:", same, flush=True)
         ok = ok and same
+# optional full-size check (BASELINE config 5): 32768^2 over the ranks, corner windows against a small-cavity oracle.
+# Information travels one node per step, so after 40 steps the nodes within 60 of a corner depend only on the two
+# walls meeting there and equal the same nodes of a 256^2 cavity with the same relaxation rate.
+if "--full" in sys.argv:
+    from oracle import lbm_oracle as O
+    n, steps, w = 32768, 40, 60
+    sc = StripCavity(n, n, 10000.0, 0.08, "float64", "MRT", overlap=True)
+    sc.step(steps, write_macros=True)
+    rho, u, f = sc.local_fields()
+    p = O.Params(256, 256, Re=10000.0 * 256 / n, collision="MRT")
+    want = O.run(p, steps, form="pull")[2]
+    errs = []
+    if rank == 0:
+        errs += [np.abs(f[:, :w, :w] - want[:, :w, :w]).max(), np.abs(f[:, -w:, :w] - want[:, -w:, :w]).max()]
+    if rank == world - 1:
+        errs += [np.abs(f[:, :w, -w:] - want[:, :w, -w:]).max(), np.abs(f[:, -w:, -w:] - want[:, -w:, -w:]).max()]
+    mass = torch.tensor([float(f.sum())], device="cuda", dtype=torch.float64)
+    dist.all_reduce(mass)
+    sc.close()
+    good = all(e <= 1e-12 for e in errs) and bool(np.isfinite(f).all())
+    print("rank", rank, "full-size corner windows max err", errs, "ok", good, flush=True)
+    if rank == 0:
+        drift = abs(float(mass.item()) / (float(n) * n) - 1.0)
+        print("full-size mean density drift after %d steps: %.3e" % (steps, drift), flush=True)
+        good = good and drift < 1e-6
+    g = torch.tensor([1 if good else 0], device="cuda")
+    dist.all_reduce(g, op=dist.ReduceOp.MIN)
+    ok = ok and int(g.item()) == 1
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
 dist.barrier()
