@@ -127,6 +127,15 @@ int lbm_mean_u(lbm_handle_t h, double* mean_out, void* stream);
  * cavities keep their populations and macros and no longer cost bandwidth; they cannot be re-activated. */
 int lbm_set_active(lbm_handle_t h, const int32_t* active, void* stream);
 
+/* Diagnostics of the stored (lagged) velocity field of one cavity, computed on the device instead of downloading the
+ * full fields as the scripts do every Pinterval (MRT_GPU.py:764-776, 793-800 / MRT.py:504-516):
+ *   ux_col    [ny_local]  u_x on the middle column x = nx/2                       (may be NULL)
+ *   uy_row    [nx]        u_y on the middle row    y = ny/2 (must be owned by this strip)  (may be NULL)
+ *   vortex_xy [4]         (x1, y1, x2, y2): argmin of |u|^2 with a border of nx/40 nodes masked, then again with a
+ *                         box of +-nx/40 around the first centre masked (whole-cavity handles only; may be NULL).
+ * Host pointers in the handle's dtype. */
+int lbm_diagnostics(lbm_handle_t h, int cavity, void* ux_col, void* uy_row, int32_t* vortex_xy, void* stream);
+
 int lbm_sync(lbm_handle_t h);
 /* Steps completed, and number of kernels this handle has launched (for the bench's gpu_launches). */
 int lbm_get_counters(lbm_handle_t h, int64_t* steps_done, int64_t* kernel_launches);

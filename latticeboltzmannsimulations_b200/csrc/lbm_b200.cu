@@ -402,6 +402,51 @@ __global__ void lbm_sum_u(const T* __restrict__ ux, const T* __restrict__ uy, do
     }
 }
 
+// Diagnostics the reference scripts compute on the host after downloading the full fields (MRT_GPU.py:764-776,
+// 793-800): centre-lines ux(x = nx/2, :) and uy(:, y = ny/2), and the vortex-centre search = argmin of |u|^2 with a
+// border of BCoffset = nx/40 nodes (and optionally a box around the first centre) masked out.
+template <typename T>
+__global__ void lbm_centerlines(const T* __restrict__ ux, const T* __restrict__ uy, T* __restrict__ ux_col,
+                                T* __restrict__ uy_row, int nx, int nyl, int pitch, int xc, int yc_local) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nyl) ux_col[i] = ux[(long long)i * pitch + xc];
+    if (yc_local >= 0 && i < nx) uy_row[i] = uy[(long long)yc_local * pitch + i];
+}
+
+struct ArgMin { double val; long long idx; };
+
+template <typename T>
+__global__ void lbm_argmin_usq(const T* __restrict__ ux, const T* __restrict__ uy, ArgMin* __restrict__ out, int nx, int ny,
+                               int pitch, int bc, int bx0, int bx1, int by0, int by1) {
+    // flat index of the reference's [x][y] array = x * ny + y; first occurrence wins on ties (np.nanargmin)
+    double best = 1e300;
+    long long bidx = -1;
+    const long long n = (long long)nx * ny;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / nx), x = (int)(i - (long long)y * nx);      // coalesced along x
+        if (x < bc || y < bc || x >= nx - 1 - bc || y >= ny - 1 - bc) continue;
+        if (x >= bx0 && x < bx1 && y >= by0 && y < by1) continue;
+        const double a = (double)ux[(long long)y * pitch + x], b = (double)uy[(long long)y * pitch + x];
+        const double v = a * a + b * b;
+        const long long flat = (long long)x * ny + y;
+        if (v < best || (v == best && flat < bidx)) { best = v; bidx = flat; }
+    }
+    __shared__ double sv[256];
+    __shared__ long long si[256];
+    sv[threadIdx.x] = best; si[threadIdx.x] = bidx;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const double v = sv[threadIdx.x + o]; const long long j = si[threadIdx.x + o];
+            if (j >= 0 && (si[threadIdx.x] < 0 || v < sv[threadIdx.x] || (v == sv[threadIdx.x] && j < si[threadIdx.x]))) {
+                sv[threadIdx.x] = v; si[threadIdx.x] = j;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[blockIdx.x].val = sv[0]; out[blockIdx.x].idx = si[0]; }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // solver object
 // ------------------------------------------------------------------------------------------------------------
@@ -1169,6 +1214,73 @@ int lbm_equilibrium(int dtype, int64_t n, const void* rho, const void* ux, const
     }
     if (d) cudaFree(d);
     if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("lbm_equilibrium: ") + cudaGetErrorString(e));
+    return LBM_OK;
+}
+
+static int argmin_pass(lbm_solver* s, int cavity, int bc, const int box[4], long long* flat, cudaStream_t st) {
+    const int nblk = 148 * 2;
+    ArgMin* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(ArgMin) * nblk));
+    const char* ux = (const char*)s->ux + (size_t)cavity * s->mplane * s->esz;
+    const char* uy = (const char*)s->uy + (size_t)cavity * s->mplane * s->esz;
+    if (s->esz == 8) lbm_argmin_usq<double><<<nblk, 256, 0, st>>>((const double*)ux, (const double*)uy, d, s->cfg.nx, s->cfg.ny, s->pitch, bc, box[0], box[1], box[2], box[3]);
+    else lbm_argmin_usq<float><<<nblk, 256, 0, st>>>((const float*)ux, (const float*)uy, d, s->cfg.nx, s->cfg.ny, s->pitch, bc, box[0], box[1], box[2], box[3]);
+    s->launches++;
+    std::vector<ArgMin> h(nblk);
+    cudaError_t e = cudaMemcpyAsync(h.data(), d, sizeof(ArgMin) * nblk, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("argmin: ") + cudaGetErrorString(e));
+    double best = 1e300; long long bi = -1;
+    for (const ArgMin& a : h)
+        if (a.idx >= 0 && (bi < 0 || a.val < best || (a.val == best && a.idx < bi))) { best = a.val; bi = a.idx; }
+    *flat = bi;
+    return LBM_OK;
+}
+
+int lbm_diagnostics(lbm_handle_t s, int cavity, void* ux_col, void* uy_row, int32_t* vortex_xy, void* stream) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    if (cavity < 0 || cavity >= s->cfg.batch) return fail(LBM_EINVAL, "cavity index out of range");
+    int rc = set_device(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nx = s->cfg.nx, ny = s->cfg.ny, nyl = s->nyl;
+    if (ux_col || uy_row) {
+        const int yc = ny / 2 - s->cfg.y0;                       // int(ysize/2), MRT_GPU.py:799
+        const bool have_row = uy_row && yc >= 0 && yc < nyl;
+        const size_t nbytes = (size_t)(nx + nyl) * s->esz;
+        rc = ensure_staging(s, nbytes);
+        if (rc) return rc;
+        char* dcol = (char*)s->staging;
+        char* drow = dcol + (size_t)nyl * s->esz;
+        const char* ux = (const char*)s->ux + (size_t)cavity * s->mplane * s->esz;
+        const char* uy = (const char*)s->uy + (size_t)cavity * s->mplane * s->esz;
+        const int n = nx > nyl ? nx : nyl;
+        if (s->esz == 8) lbm_centerlines<double><<<(n + 255) / 256, 256, 0, st>>>((const double*)ux, (const double*)uy, (double*)dcol, (double*)drow, nx, nyl, s->pitch, nx / 2, have_row ? yc : -1);
+        else lbm_centerlines<float><<<(n + 255) / 256, 256, 0, st>>>((const float*)ux, (const float*)uy, (float*)dcol, (float*)drow, nx, nyl, s->pitch, nx / 2, have_row ? yc : -1);
+        s->launches++;
+        CK(cudaGetLastError());
+        if (ux_col) CK(cudaMemcpyAsync(ux_col, dcol, (size_t)nyl * s->esz, cudaMemcpyDeviceToHost, st));
+        if (have_row) CK(cudaMemcpyAsync(uy_row, drow, (size_t)nx * s->esz, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (uy_row && !have_row) return fail(LBM_ESTATE, "row y = ny/2 is not owned by this y-strip");
+    }
+    if (vortex_xy) {
+        if (nyl != ny) return fail(LBM_ESTATE, "the vortex search needs the whole cavity in one handle");
+        const int bc = nx / 40;                                   // BCoffset, MRT_GPU.py:767
+        const int none[4] = {0, 0, 0, 0};
+        long long f1 = -1, f2 = -1;
+        rc = argmin_pass(s, cavity, bc, none, &f1, st);
+        if (rc) return rc;
+        if (f1 < 0) return fail(LBM_ESTATE, "cavity too small for the vortex search (everything masked)");
+        const int x1 = (int)(f1 / ny), y1 = (int)(f1 % ny);
+        const int box[4] = {x1 - bc, x1 + bc, y1 - bc, y1 + bc};  // MRT_GPU.py:774
+        rc = argmin_pass(s, cavity, bc, box, &f2, st);
+        if (rc) return rc;
+        vortex_xy[0] = x1; vortex_xy[1] = y1;
+        vortex_xy[2] = f2 < 0 ? -1 : (int)(f2 / ny);
+        vortex_xy[3] = f2 < 0 ? -1 : (int)(f2 % ny);
+    }
     return LBM_OK;
 }
 

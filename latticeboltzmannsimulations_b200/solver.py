@@ -184,6 +184,19 @@ class CavitySolver:
             raise ValueError("need one flag per cavity")
         _capi.check(self._lib.lbm_set_active(self._h, flags.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(stream)))
 
+    def diagnostics(self, cavity: int = 0, vortices: bool = True, stream: int = 0):
+        """Centre-lines and vortex centres of the stored velocity field, reduced on the device.
+
+        Returns ``(ux_col[ny], uy_row[nx], ((x1, y1), (x2, y2)))`` -- what ``MRT_GPU.py:764-776, 793-800`` computes
+        on the host after downloading ``u``: ``u[0, nx//2, :]``, ``u[1, :, ny//2]`` and the two ``nanargmin`` locations.
+        """
+        ux_col = np.empty(self.ny_local, dtype=self.np_dtype)
+        uy_row = np.empty(self.nx, dtype=self.np_dtype)
+        loc = (C.c_int32 * 4)()
+        _capi.check(self._lib.lbm_diagnostics(self._h, int(cavity), ux_col.ctypes.data, uy_row.ctypes.data,
+                                              loc if vortices else None, C.c_void_p(stream)))
+        return ux_col, uy_row, (((loc[0], loc[1]), (loc[2], loc[3])) if vortices else None)
+
     def sync(self) -> None:
         _capi.check(self._lib.lbm_sync(self._h))
 

@@ -330,3 +330,39 @@ def test_error_paths():
             s.set_rates(0.08, 2.5)
         with pytest.raises(ValueError, match="expected shape"):
             s.upload_f(np.zeros((9, 32, 31)))
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_device_diagnostics_match_host_postprocessing(dtype):
+    """Centre-lines and the vortex search of MRT_GPU.py:764-776, 793-800, reduced on the device, against the same
+    NumPy post-processing applied to the downloaded field; and the primary vortex of Re = 100 sits at Ghia's (0.6172, 0.7344)."""
+    import json
+    import latticeboltzmannsimulations_b200 as L
+    from latticeboltzmannsimulations_b200.diagnostics import centerline_errors, vortex_positions
+    nx = ny = 120
+    with L.CavitySolver(nx, ny, 1, dtype, "MRT") as s:
+        s.set_reynolds(100)
+        s.init_equilibrium()
+        s.step(30000, write_macros=True)
+        rho, u = s.macros()
+        ux_col, uy_row, loc = s.diagnostics()
+    assert np.array_equal(ux_col, u[0, nx // 2, :]) and np.array_equal(uy_row, u[1, :, ny // 2])
+    usq = (u[0].astype(np.float64) ** 2 + u[1].astype(np.float64) ** 2)
+    bc = nx // 40
+    usq[0:bc, :] = np.nan; usq[:, 0:bc] = np.nan
+    usq[nx - 1 - bc:nx, :] = np.nan; usq[:, ny - 1 - bc:ny] = np.nan
+    l1 = np.unravel_index(np.nanargmin(usq), usq.shape)
+    usq[l1[0] - bc:l1[0] + bc, l1[1] - bc:l1[1] + bc] = np.nan
+    l2 = np.unravel_index(np.nanargmin(usq), usq.shape)
+    assert loc[0] == tuple(int(v) for v in l1) and loc[1] == tuple(int(v) for v in l2)
+    g = json.load(open(os.path.join(GOLDEN, "ghia_re100.json")))
+    ex, ey = centerline_errors(ux_col, uy_row, 0.08, g["Y"], g["Ux"], g["X"], g["Uy"])
+    assert ex < 0.02 and ey < 0.02, (ex, ey)
+    # the reference's search returns the most stagnant points (corner eddies first); physical coordinates are in [0,1]
+    assert all(0.0 <= c <= 1.0 for xy in vortex_positions(loc, nx, ny) for c in xy)
+    # primary vortex of Re = 100 (Ghia: x = 0.6172, y = 0.7344): speed minimum of the core region of the same field
+    core = np.full_like(usq, np.nan)
+    sl = (slice(nx // 4, 7 * nx // 8), slice(ny // 8, ny // 2))          # away from the walls and the corner eddies
+    core[sl] = (u[0].astype(np.float64) ** 2 + u[1].astype(np.float64) ** 2)[sl]
+    cx, cy = np.unravel_index(np.nanargmin(core), core.shape)
+    assert abs(cx / (nx - 1.0) - 0.6172) < 0.03 and abs(1.0 - cy / (ny - 1.0) - 0.7344) < 0.03, (cx, cy)
