@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) lbm_step_ldg(const StepArgs a) {
             const long long m = (long long)b * a.mplane + (long long)yl * a.pitch + x;
             T* pi = static_cast<T*>(a.pi_eq) + m;
             T* rp = static_cast<T*>(a.rho_prev) + m;
-            const T om = smagorinsky_omega<T>(f, *pi, *rp, r.omega);
+            const T om = smagorinsky_omega<T>(f, *pi, *rp, r.tau0);
             T pi_new;
             node_update<T, COLL, MACROS, true>(f, r, left, right, lid, bot, rho, ux, uy, om, &pi_new);
             *pi = pi_new;
@@ -156,7 +156,7 @@ __device__ __forceinline__ void gstore(T* p, const T in[V]) {
     *reinterpret_cast<VT*>(p) = v;
 }
 
-template <typename T, int COLL, bool MACROS, int V>
+template <typename T, int COLL, bool MACROS, int V, bool TURB = false>
 __global__ void __launch_bounds__(256) lbm_step_vec(const StepArgs a) {
     const int lane = threadIdx.x & 31;                                  // blockDim.x is a multiple of 32: a warp is one row
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * V;          // first node of this thread
@@ -220,6 +220,12 @@ __global__ void __launch_bounds__(256) lbm_step_vec(const StepArgs a) {
         f[v][7] = v == V - 1 ? h7 : v7[v + 1];
     }
     T rho[V], ux[V], uy[V];
+    T pi_old[V], rp_old[V], pi_new[V];
+    if (TURB) {   // previous-step sum cx cy feq and rho of these nodes (pitch padding keeps the vector access in bounds)
+        const long long m = (long long)b * a.mplane + (long long)yl * a.pitch + x;
+        gload<T, V>(static_cast<const T*>(a.pi_eq) + m, pi_old);
+        gload<T, V>(static_cast<const T*>(a.rho_prev) + m, rp_old);
+    }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         const int xv = x + v;
@@ -232,7 +238,24 @@ __global__ void __launch_bounds__(256) lbm_step_vec(const StepArgs a) {
             wall_rule<T>(f[v], left, right, lid, bot, rl, r.uLB, stale);
             if (slot >= 0) carry[slot] = corner_value<T>(f[v], slot);
         }
-        node_update<T, COLL, MACROS>(f[v], r, left, right, lid, bot, rho[v], ux[v], uy[v]);
+        if (TURB) pi_new[v] = (T)0;
+        if (TURB) {
+            const T om = smagorinsky_omega<T>(f[v], pi_old[v], rp_old[v], r.tau0);
+            node_update<T, COLL, MACROS, true>(f[v], r, left, right, lid, bot, rho[v], ux[v], uy[v], om, &pi_new[v]);
+        } else {
+            node_update<T, COLL, MACROS>(f[v], r, left, right, lid, bot, rho[v], ux[v], uy[v]);
+        }
+    }
+    if (TURB) {
+        const long long m = (long long)b * a.mplane + (long long)yl * a.pitch + x;
+        if (x + V <= a.nx) {
+            gstore<T, V>(static_cast<T*>(a.pi_eq) + m, pi_new);
+            gstore<T, V>(static_cast<T*>(a.rho_prev) + m, rho);
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (x + v < a.nx) { static_cast<T*>(a.pi_eq)[m + v] = pi_new[v]; static_cast<T*>(a.rho_prev)[m + v] = rho[v]; }
+        }
     }
     if (lid) {
 #pragma unroll
@@ -679,8 +702,13 @@ template <typename T, int COLL, int V>
 static void launch_vec_flags(const StepArgs& a, int nx, int rows, int batch, cudaStream_t st, bool macros) {
     dim3 block, grid;
     block_shape((nx + V - 1) / V, rows, &block, &grid, batch);
-    if (macros) lbm_step_vec<T, COLL, true, V><<<grid, block, 0, st>>>(a);
-    else lbm_step_vec<T, COLL, false, V><<<grid, block, 0, st>>>(a);
+    if (a.pi_eq) {
+        if (macros) lbm_step_vec<T, COLL, true, V, true><<<grid, block, 0, st>>>(a);
+        else lbm_step_vec<T, COLL, false, V, true><<<grid, block, 0, st>>>(a);
+    } else {
+        if (macros) lbm_step_vec<T, COLL, true, V><<<grid, block, 0, st>>>(a);
+        else lbm_step_vec<T, COLL, false, V><<<grid, block, 0, st>>>(a);
+    }
 }
 template <typename T, int V>
 static void launch_vec_coll(int coll, const StepArgs& a, int nx, int rows, int batch, cudaStream_t st, bool macros) {
@@ -722,7 +750,7 @@ static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin,
         return LBM_OK;
     }
     const int vw = s->cfg.dtype == LBM_F64 ? s->vec_f64 : s->vec_f32;
-    if (mode == MODE_STEP && gather && vw > 1 && !s->cfg.turb) {
+    if (mode == MODE_STEP && gather && vw > 1) {
         if (s->cfg.dtype == LBM_F64) launch_vec_coll<double, 2>(s->cfg.collision, a, s->cfg.nx, row_count, s->cfg.batch, st, macros);
         else if (vw == 4) launch_vec_coll<float, 4>(s->cfg.collision, a, s->cfg.nx, row_count, s->cfg.batch, st, macros);
         else launch_vec_coll<float, 2>(s->cfg.collision, a, s->cfg.nx, row_count, s->cfg.batch, st, macros);
@@ -920,6 +948,7 @@ int lbm_set_rates(lbm_handle_t s, int cavity, double uLB, double omega_nu, doubl
         CavityParams& p = s->cav_host[b];
         p.uLB = uLB; p.omega = omega_nu; p.omegam = omega_minus;
         p.s_e = omega_e; p.s_eps = omega_eps; p.s_q = omega_q;
+        p.tau0 = 1.0 / omega_nu;
     }
     s->cav_dirty = true;
     return LBM_OK;

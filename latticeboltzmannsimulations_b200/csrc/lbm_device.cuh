@@ -22,7 +22,8 @@ struct CavityParams {
     double omega;      // SRT omega / TRT omega+ / MRT omega_nu   (MRT_GPU.py:65, 82, 88)
     double omegam;     // TRT omega-                              (MRT_GPU.py:84)
     double s_e, s_eps, s_q;                                    // (MRT_GPU.py:89-91)
-    double pad[2];
+    double tau0;       // 1 / omega, the molecular relaxation time entering the Smagorinsky closure (MRT_GPU.py:553)
+    double pad;
 };
 
 // Kernel arguments shared by every kernel family (device pointers are untyped: dtype is a template parameter).
@@ -47,9 +48,10 @@ struct StepArgs {
 
 template <typename T>
 struct Rates {
-    T uLB, omega, omegam, s_e, s_eps, s_q;
+    T uLB, omega, omegam, s_e, s_eps, s_q, tau0;
     __device__ __forceinline__ explicit Rates(const CavityParams& p)
-        : uLB((T)p.uLB), omega((T)p.omega), omegam((T)p.omegam), s_e((T)p.s_e), s_eps((T)p.s_eps), s_q((T)p.s_q) {}
+        : uLB((T)p.uLB), omega((T)p.omega), omegam((T)p.omegam), s_e((T)p.s_e), s_eps((T)p.s_eps), s_q((T)p.s_q),
+          tau0((T)p.tau0) {}
 };
 
 // Lattice weights t_k (MRT.py:144-146).
@@ -279,10 +281,9 @@ __device__ __forceinline__ void collide_mrt(T f[9], T rho, T s_e, T s_eps, T s_q
 // Q = sum_k cx cy (f_k - feq_k^prev), with feq and rho of the PREVIOUS step (the reference reads feq_g / rho_g before
 // overwriting them) and Cs2 hard-set to 0.025 (:578; the Van-Driest lines above it are dead code).
 template <typename T>
-__device__ __forceinline__ T smagorinsky_omega(const T f[9], T pi_prev, T rho_prev, T omega) {
+__device__ __forceinline__ T smagorinsky_omega(const T f[9], T pi_prev, T rho_prev, T tau0) {
     const T product1 = f[5] - f[6] + f[7] - f[8];
     const T Qmf = product1 - pi_prev;
-    const T tau0 = (T)1.0 / omega;
     const T tau = (T)0.5 * (tau0 + sqrt(tau0 * tau0 + ((T)(18 * 1.4142 * 0.025) * fabs(Qmf)) / rho_prev));
     return (T)1.0 / tau;
 }
@@ -296,7 +297,7 @@ __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left
     moments_ref<T>(f, rho, jx, jy);
     T ux = (T)0, uy = (T)0;
     if (NEED_U || TURB || COLL != COLL_MRT) {
-        if (sizeof(T) == 4) {            // fp32: one reciprocal + two multiplies (the fp64 path keeps true divisions)
+        if (sizeof(T) == 4 || (TURB && COLL == COLL_MRT)) {   // one reciprocal + two multiplies (fp64 SRT/TRT keep true divisions)
             const T inv = (T)1 / rho;
             ux = jx * inv;
             uy = jy * inv;

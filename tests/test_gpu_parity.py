@@ -366,3 +366,14 @@ def test_device_diagnostics_match_host_postprocessing(dtype):
     core[sl] = (u[0].astype(np.float64) ** 2 + u[1].astype(np.float64) ** 2)[sl]
     cx, cy = np.unravel_index(np.nanargmin(core), core.shape)
     assert abs(cx / (nx - 1.0) - 0.6172) < 0.03 and abs(1.0 - cy / (ny - 1.0) - 0.7344) < 0.03, (cx, cy)
+
+
+@pytest.mark.parametrize("nx,ny", [(3, 3), (4, 5), (3, 40), (37, 3)])
+def test_minimum_sizes(nx, ny):
+    """Smallest legal cavities (every node is a wall node) against the oracle, both dtypes."""
+    import latticeboltzmannsimulations_b200 as L
+    p = O.Params(nx, ny, Re=50, collision="MRT")
+    want = O.run(p, 25, form="push")
+    for dtype in ("float64", "float32"):
+        got = L.run_cavity(nx, ny, 50, steps=25, dtype=dtype, return_f=True)
+        assert_close(got, want, dtype, what="%dx%d" % (nx, ny))
