@@ -126,17 +126,15 @@ def cpu_step_timer(variant: str):
                 rho, u, fin, feq = F.allfunc(rho, u, fin, feq)           # :453
             return time.perf_counter() - t
         return "reference", cores, run
-    from oracle import lbm_oracle as O
+    from oracle import lbm_oracle as O       # no compiled reference here: time the oracle's C restatement instead
 
     def run(n, Re, steps):
         p = O.Params(n, n, Re=Re, collision="MRT")
-        ps = O.PullState.from_fin(O.init_fields(n, n, 0.08)[2], p)
-        O.step_C_pull(ps, p)
+        O.run_fast(p, 1)
         t = time.perf_counter()
-        for _ in range(steps):
-            O.step_C_pull(ps, p)
+        O.run_fast(p, steps)
         return time.perf_counter() - t
-    return "port", 1, run
+    return "port", os.cpu_count() or 1, run
 
 
 def cpu_baseline_sample(variant: str, Re: float, budget_s: float, n: int):

@@ -638,3 +638,31 @@ def ghia_errors(u: np.ndarray, uLB: float, ghia) -> Tuple[float, float]:
 
 
 GHIA_JSON = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "ghia_re100.json")
+
+
+# --------------------------------------------------------------------------------------------
+# Fast path: the same step_C compiled from oracle/lbm_oracle_c.c (bit-identical, multi-threaded)
+# --------------------------------------------------------------------------------------------
+def run_fast(p: Params, steps: int, fin0: Optional[np.ndarray] = None):
+    """``run(p, steps, semantics='C', form='push')`` through the C restatement; falls back to NumPy if gcc is absent."""
+    import ctypes as C_
+    try:
+        from . import build_oracle_c
+        lib = C_.CDLL(build_oracle_c.build())
+    except Exception:
+        return run(p, steps, semantics="C", fin0=fin0, form="push")
+
+    class _P(C_.Structure):
+        _fields_ = [("nx", C_.c_int), ("ny", C_.c_int), ("collision", C_.c_int), ("turb", C_.c_int),
+                    ("uLB", C_.c_double), ("omega", C_.c_double), ("omega_e", C_.c_double),
+                    ("omega_eps", C_.c_double), ("omega_q", C_.c_double), ("omegam", C_.c_double)]
+
+    st = StateC.initial(p, fin0)
+    cp = _P(p.nx, p.ny, {"SRT": 0, "TRT": 1, "MRT": 2}[p.collision], int(p.turb), p.uLB, p.omega, p.omega_e,
+            p.omega_eps, p.omega_q, p.omegam)
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (st.fin, st.ftemp, st.feq, st.rho, st.u)]
+    dp = C_.POINTER(C_.c_double)
+    lib.oracle_step_C.argtypes = [C_.POINTER(_P)] + [dp] * 5 + [C_.c_int]
+    lib.oracle_step_C.restype = None
+    lib.oracle_step_C(C_.byref(cp), *[a.ctypes.data_as(dp) for a in arrs], int(steps))
+    return arrs[3], arrs[4], arrs[0]

@@ -103,23 +103,32 @@ def test_single_steps_every_boundary_class(n):
 
 
 def test_config2_parity_384_Re3200():
-    """BASELINE config 2: 384x384, Re 3200, fp64, N in {1, 10, 100, 1000} against the oracle."""
+    """BASELINE config 2: 384x384, Re 3200, fp64, N in {1, 10, 100, 1000} against the oracle (C restatement of the
+    oracle, bit-identical to the NumPy one -- tests/test_oracle.py -- so that 1111 steps of 384^2 take seconds)."""
     import latticeboltzmannsimulations_b200 as L
     nx = ny = 384
     p = O.Params(nx, ny, Re=3200, collision="MRT")
-    ps = O.PullState.from_fin(O.init_fields(nx, ny, 0.08)[2], p)
-    done = 0
     with L.CavitySolver(nx, ny, 1, "float64", "MRT") as s:
         s.set_reynolds(3200, 0.08)
         s.init_equilibrium()
         for n in (1, 10, 100, 1000):
-            while done < n:
-                O.step_C_pull(ps, p)
-                done += 1
+            want = O.run_fast(p, n)
             s.step(n - s.counters()[0], write_macros=True)
             rho, u = s.macros()
             f = s.download_f()
-            assert_close((rho, u, f), (ps.rho, ps.u, O.fin_from_pull(ps, p)), "float64", what="N=%d" % n)
+            assert_close((rho, u, f), want, "float64", what="N=%d" % n)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("coll", ["MRT", "SRT"])
+def test_large_grid_against_oracle(coll, dtype):
+    """1024 x 768 (beyond L2 for fp64 A/B), Re 5000, 200 steps: full-field comparison with the oracle."""
+    import latticeboltzmannsimulations_b200 as L
+    nx, ny, n = 1024, 768, 200
+    p = O.Params(nx, ny, Re=5000, collision=coll)
+    want = O.run_fast(p, n)
+    got = L.run_cavity(nx, ny, 5000, steps=n, collision=coll, dtype=dtype, return_f=True)
+    assert_close(got, want, dtype, what="%s 1024x768" % coll)
 
 
 def test_ghia_re100_128():

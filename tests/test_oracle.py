@@ -68,6 +68,18 @@ def test_pull_form_is_the_push_form(coll, turb, shape):
             assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize("coll", ["SRT", "TRT", "MRT"])
+@pytest.mark.parametrize("turb", [0, 1])
+def test_c_restatement_equals_numpy_oracle(coll, turb):
+    """oracle/lbm_oracle_c.c (threaded, used for the larger parity cases) reproduces the NumPy oracle bit for bit."""
+    for (nx, ny, f0) in ((40, 28, O.random_state(40, 28, 3)), (33, 65, None)):
+        p = O.Params(nx, ny, Re=400, collision=coll, turb=turb)
+        a = O.run(p, 50, fin0=f0, form="push")
+        b = O.run_fast(p, 50, fin0=f0)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+
+
 def test_moment_basis_inverse():
     assert np.abs(O.M_GS @ O.M_GS_INV - np.eye(9)).max() <= 2.3e-16     # MRT.py:163-183
 
