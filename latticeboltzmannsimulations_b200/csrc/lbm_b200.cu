@@ -46,6 +46,10 @@ static int fail(int code, const std::string& msg) {
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, int COLL, bool GATHER, bool MACROS, int MODE, bool TURB = false>
 __global__ void __launch_bounds__(256) lbm_step_ldg(const StepArgs a) {
+    // programmatic dependent launch: let the next step's grid be scheduled, then wait for the previous grid
+    // (no-ops for ordinary launches)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int lr = blockIdx.y * blockDim.y + threadIdx.y;          // launch row
     if (x >= a.nx || lr >= a.row_count) return;
@@ -158,6 +162,8 @@ __device__ __forceinline__ void gstore(T* p, const T in[V]) {
 
 template <typename T, int COLL, bool MACROS, int V, bool TURB = false>
 __global__ void __launch_bounds__(256) lbm_step_vec(const StepArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;                                  // blockDim.x is a multiple of 32: a warp is one row
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * V;          // first node of this thread
     const int lr = blockIdx.y * blockDim.y + threadIdx.y;               // launch row (warp-uniform)
@@ -515,6 +521,7 @@ struct lbm_solver {
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     cudaStream_t capture_stream = nullptr;
     int use_graph = 1;
+    int use_pdl = 1;
 };
 
 // A fresh state (init / upload) un-freezes every cavity; graphs captured with the old flag pointer are dropped.
@@ -643,20 +650,39 @@ static cudaError_t launch_tma_coll(lbm_solver* s, const CUtensorMap* tm, const S
 
 // ---- kernel dispatch ----------------------------------------------------------------------------------------
 static thread_local dim3 g_block(256, 1, 1);      // block shape of the scalar family for the current launch
+static thread_local bool g_pdl = false;           // launch the step kernels with programmatic stream serialization
+
+// Launch a step kernel.  With g_pdl the launch carries cudaLaunchAttributeProgrammaticStreamSerialization: the next
+// step's CTAs may be scheduled while this one drains; they block in griddepcontrol.wait (first instruction of the
+// kernels) until the previous grid has completed and flushed, so the A/B read/write ordering is unchanged.
+template <typename K>
+static void launch_step(K kern, dim3 grid, dim3 block, cudaStream_t st, const StepArgs& a) {
+    if (!g_pdl) {
+        kern<<<grid, block, 0, st>>>(a);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, a);
+}
 
 template <typename T, int COLL, bool GATHER, bool MACROS, int MODE>
 static void launch_ldg(const StepArgs& a, dim3 grid, cudaStream_t st) {
-    lbm_step_ldg<T, COLL, GATHER, MACROS, MODE><<<grid, g_block, 0, st>>>(a);
+    launch_step(lbm_step_ldg<T, COLL, GATHER, MACROS, MODE>, grid, g_block, st, a);
 }
 
 template <typename T, int COLL, bool TURB>
 static void dispatch_step(const StepArgs& a, dim3 grid, cudaStream_t st, bool gather, bool macros) {
     if (gather) {
-        if (macros) lbm_step_ldg<T, COLL, true, true, MODE_STEP, TURB><<<grid, g_block, 0, st>>>(a);
-        else lbm_step_ldg<T, COLL, true, false, MODE_STEP, TURB><<<grid, g_block, 0, st>>>(a);
+        if (macros) launch_step(lbm_step_ldg<T, COLL, true, true, MODE_STEP, TURB>, grid, g_block, st, a);
+        else launch_step(lbm_step_ldg<T, COLL, true, false, MODE_STEP, TURB>, grid, g_block, st, a);
     } else {
-        if (macros) lbm_step_ldg<T, COLL, false, true, MODE_STEP, TURB><<<grid, g_block, 0, st>>>(a);
-        else lbm_step_ldg<T, COLL, false, false, MODE_STEP, TURB><<<grid, g_block, 0, st>>>(a);
+        if (macros) launch_step(lbm_step_ldg<T, COLL, false, true, MODE_STEP, TURB>, grid, g_block, st, a);
+        else launch_step(lbm_step_ldg<T, COLL, false, false, MODE_STEP, TURB>, grid, g_block, st, a);
     }
 }
 
@@ -703,11 +729,11 @@ static void launch_vec_flags(const StepArgs& a, int nx, int rows, int batch, cud
     dim3 block, grid;
     block_shape((nx + V - 1) / V, rows, &block, &grid, batch);
     if (a.pi_eq) {
-        if (macros) lbm_step_vec<T, COLL, true, V, true><<<grid, block, 0, st>>>(a);
-        else lbm_step_vec<T, COLL, false, V, true><<<grid, block, 0, st>>>(a);
+        if (macros) launch_step(lbm_step_vec<T, COLL, true, V, true>, grid, block, st, a);
+        else launch_step(lbm_step_vec<T, COLL, false, V, true>, grid, block, st, a);
     } else {
-        if (macros) lbm_step_vec<T, COLL, true, V><<<grid, block, 0, st>>>(a);
-        else lbm_step_vec<T, COLL, false, V><<<grid, block, 0, st>>>(a);
+        if (macros) launch_step(lbm_step_vec<T, COLL, true, V>, grid, block, st, a);
+        else launch_step(lbm_step_vec<T, COLL, false, V>, grid, block, st, a);
     }
 }
 template <typename T, int V>
@@ -737,6 +763,7 @@ static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin,
         return LBM_OK;
     }
     a.row_count = row_count;
+    g_pdl = s->use_pdl && mode == MODE_STEP;
     dim3 grid;
     block_shape(s->cfg.nx, row_count, &g_block, &grid, s->cfg.batch);
     if (grid.y > 65535u || grid.z > 65535u) {
@@ -876,6 +903,7 @@ int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
     if (const char* ev = getenv("LBM_B200_VEC_F64")) s->vec_f64 = atoi(ev) == 2 ? 2 : 1;
     if (const char* ev = getenv("LBM_B200_VEC_F32")) s->vec_f32 = (atoi(ev) == 2 || atoi(ev) == 4) ? atoi(ev) : 1;
     if (const char* ev = getenv("LBM_B200_GRAPH")) s->use_graph = atoi(ev) != 0;
+    if (const char* ev = getenv("LBM_B200_PDL")) s->use_pdl = atoi(ev) != 0;
     if (const char* ev = getenv("LBM_B200_TMA_VARIANT")) s->tma_variant = atoi(ev) % LBM_TMA_VARIANTS;
     if (const char* ev = getenv("LBM_B200_TMA_CTAS")) s->tma_ctas_per_sm = atoi(ev) > 0 ? atoi(ev) : 1;
 #define CKD(call)                                                                       \
