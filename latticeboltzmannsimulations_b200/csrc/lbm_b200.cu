@@ -588,7 +588,7 @@ static int make_tensor_maps(lbm_solver* s) {
     cuuint32_t estr[2] = {1, 1};
     for (int i = 0; i < 2; ++i) {
         for (int w = 0; w < 2; ++w) {
-            cuuint32_t box[2] = {(cuuint32_t)(txn + (w ? V : 0)), (cuuint32_t)ty};
+            cuuint32_t box[2] = {(cuuint32_t)(txn + (w ? 128 / s->esz : 0)), (cuuint32_t)ty};
             CUresult r = encode(&s->tmap[i][w],
                                 s->esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, s->f[i],
                                 dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -649,20 +649,23 @@ static cudaError_t launch_tma_coll(lbm_solver* s, const CUtensorMap* tm, const S
 }
 
 // ---- kernel dispatch ----------------------------------------------------------------------------------------
-static thread_local dim3 g_block(256, 1, 1);      // block shape of the scalar family for the current launch
-static thread_local bool g_pdl = false;           // launch the step kernels with programmatic stream serialization
+struct Launch {
+    dim3 grid, block;
+    cudaStream_t st;
+    bool pdl;          // launch with programmatic stream serialization (step kernels only)
+};
 
-// Launch a step kernel.  With g_pdl the launch carries cudaLaunchAttributeProgrammaticStreamSerialization: the next
+// Launch a step kernel.  With L.pdl the launch carries cudaLaunchAttributeProgrammaticStreamSerialization: the next
 // step's CTAs may be scheduled while this one drains; they block in griddepcontrol.wait (first instruction of the
 // kernels) until the previous grid has completed and flushed, so the A/B read/write ordering is unchanged.
 template <typename K>
-static void launch_step(K kern, dim3 grid, dim3 block, cudaStream_t st, const StepArgs& a) {
-    if (!g_pdl) {
-        kern<<<grid, block, 0, st>>>(a);
+static void launch_step(K kern, const Launch& L, const StepArgs& a) {
+    if (!L.pdl) {
+        kern<<<L.grid, L.block, 0, L.st>>>(a);
         return;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cfg.gridDim = L.grid; cfg.blockDim = L.block; cfg.dynamicSmemBytes = 0; cfg.stream = L.st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -670,47 +673,42 @@ static void launch_step(K kern, dim3 grid, dim3 block, cudaStream_t st, const St
     cudaLaunchKernelEx(&cfg, kern, a);
 }
 
-template <typename T, int COLL, bool GATHER, bool MACROS, int MODE>
-static void launch_ldg(const StepArgs& a, dim3 grid, cudaStream_t st) {
-    launch_step(lbm_step_ldg<T, COLL, GATHER, MACROS, MODE>, grid, g_block, st, a);
-}
-
 template <typename T, int COLL, bool TURB>
-static void dispatch_step(const StepArgs& a, dim3 grid, cudaStream_t st, bool gather, bool macros) {
+static void dispatch_step(const StepArgs& a, const Launch& L, bool gather, bool macros) {
     if (gather) {
-        if (macros) launch_step(lbm_step_ldg<T, COLL, true, true, MODE_STEP, TURB>, grid, g_block, st, a);
-        else launch_step(lbm_step_ldg<T, COLL, true, false, MODE_STEP, TURB>, grid, g_block, st, a);
+        if (macros) launch_step(lbm_step_ldg<T, COLL, true, true, MODE_STEP, TURB>, L, a);
+        else launch_step(lbm_step_ldg<T, COLL, true, false, MODE_STEP, TURB>, L, a);
     } else {
-        if (macros) launch_step(lbm_step_ldg<T, COLL, false, true, MODE_STEP, TURB>, grid, g_block, st, a);
-        else launch_step(lbm_step_ldg<T, COLL, false, false, MODE_STEP, TURB>, grid, g_block, st, a);
+        if (macros) launch_step(lbm_step_ldg<T, COLL, false, true, MODE_STEP, TURB>, L, a);
+        else launch_step(lbm_step_ldg<T, COLL, false, false, MODE_STEP, TURB>, L, a);
     }
 }
 
 template <typename T, int COLL>
-static void dispatch_flags(const StepArgs& a, dim3 grid, cudaStream_t st, bool gather, bool macros, int mode) {
-    if (mode == MODE_FINALIZE) { launch_ldg<T, COLL, true, false, MODE_FINALIZE>(a, grid, st); return; }
+static void dispatch_flags(const StepArgs& a, const Launch& L, bool gather, bool macros, int mode) {
+    if (mode == MODE_FINALIZE) { launch_step(lbm_step_ldg<T, COLL, true, false, MODE_FINALIZE>, L, a); return; }
     if (mode == MODE_MACROS) {
-        if (gather) launch_ldg<T, COLL, true, true, MODE_MACROS>(a, grid, st);
-        else launch_ldg<T, COLL, false, true, MODE_MACROS>(a, grid, st);
+        if (gather) launch_step(lbm_step_ldg<T, COLL, true, true, MODE_MACROS>, L, a);
+        else launch_step(lbm_step_ldg<T, COLL, false, true, MODE_MACROS>, L, a);
         return;
     }
-    if (a.pi_eq) dispatch_step<T, COLL, true>(a, grid, st, gather, macros);
-    else dispatch_step<T, COLL, false>(a, grid, st, gather, macros);
+    if (a.pi_eq) dispatch_step<T, COLL, true>(a, L, gather, macros);
+    else dispatch_step<T, COLL, false>(a, L, gather, macros);
 }
 
 template <typename T>
-static void dispatch_coll(int coll, const StepArgs& a, dim3 grid, cudaStream_t st, bool gather, bool macros, int mode) {
-    if (mode != MODE_STEP) { dispatch_flags<T, COLL_MRT>(a, grid, st, gather, macros, mode); return; }
+static void dispatch_coll(int coll, const StepArgs& a, const Launch& L, bool gather, bool macros, int mode) {
+    if (mode != MODE_STEP) { dispatch_flags<T, COLL_MRT>(a, L, gather, macros, mode); return; }
     switch (coll) {
-        case LBM_SRT: dispatch_flags<T, COLL_SRT>(a, grid, st, gather, macros, mode); break;
-        case LBM_TRT: dispatch_flags<T, COLL_TRT>(a, grid, st, gather, macros, mode); break;
-        default: dispatch_flags<T, COLL_MRT>(a, grid, st, gather, macros, mode); break;
+        case LBM_SRT: dispatch_flags<T, COLL_SRT>(a, L, gather, macros, mode); break;
+        case LBM_TRT: dispatch_flags<T, COLL_TRT>(a, L, gather, macros, mode); break;
+        default: dispatch_flags<T, COLL_MRT>(a, L, gather, macros, mode); break;
     }
 }
 
 // Block shape for `threads_x` threads along a row: blockDim.x from {256,...,32} with the least idle lanes (ties go
 // to the wider block), blockDim.y rows so that a block has up to 256 threads.
-static void block_shape(int threads_x, int rows, dim3* block, dim3* grid, int batch) {
+static void block_shape(int threads_x, int rows, int batch, Launch* L) {
     int best = 256, waste = 1 << 30;
     for (int bx = 256; bx >= 32; bx -= 32) {
         const int w = (threads_x + bx - 1) / bx * bx - threads_x;
@@ -719,29 +717,27 @@ static void block_shape(int threads_x, int rows, dim3* block, dim3* grid, int ba
     int by = 256 / best;
     if (by > rows) by = rows;
     if (by < 1) by = 1;
-    *block = dim3(best, by, 1);
-    *grid = dim3((threads_x + best - 1) / best, (rows + by - 1) / by, batch);
+    L->block = dim3(best, by, 1);
+    L->grid = dim3((threads_x + best - 1) / best, (rows + by - 1) / by, batch);
 }
 
 // ---- vector ldg dispatch (hot path) ---------------------------------------------------------------------------
 template <typename T, int COLL, int V>
-static void launch_vec_flags(const StepArgs& a, int nx, int rows, int batch, cudaStream_t st, bool macros) {
-    dim3 block, grid;
-    block_shape((nx + V - 1) / V, rows, &block, &grid, batch);
+static void launch_vec_flags(const StepArgs& a, const Launch& L, bool macros) {
     if (a.pi_eq) {
-        if (macros) launch_step(lbm_step_vec<T, COLL, true, V, true>, grid, block, st, a);
-        else launch_step(lbm_step_vec<T, COLL, false, V, true>, grid, block, st, a);
+        if (macros) launch_step(lbm_step_vec<T, COLL, true, V, true>, L, a);
+        else launch_step(lbm_step_vec<T, COLL, false, V, true>, L, a);
     } else {
-        if (macros) launch_step(lbm_step_vec<T, COLL, true, V>, grid, block, st, a);
-        else launch_step(lbm_step_vec<T, COLL, false, V>, grid, block, st, a);
+        if (macros) launch_step(lbm_step_vec<T, COLL, true, V>, L, a);
+        else launch_step(lbm_step_vec<T, COLL, false, V>, L, a);
     }
 }
 template <typename T, int V>
-static void launch_vec_coll(int coll, const StepArgs& a, int nx, int rows, int batch, cudaStream_t st, bool macros) {
+static void launch_vec_coll(int coll, const StepArgs& a, const Launch& L, bool macros) {
     switch (coll) {
-        case LBM_SRT: launch_vec_flags<T, COLL_SRT, V>(a, nx, rows, batch, st, macros); break;
-        case LBM_TRT: launch_vec_flags<T, COLL_TRT, V>(a, nx, rows, batch, st, macros); break;
-        default: launch_vec_flags<T, COLL_MRT, V>(a, nx, rows, batch, st, macros); break;
+        case LBM_SRT: launch_vec_flags<T, COLL_SRT, V>(a, L, macros); break;
+        case LBM_TRT: launch_vec_flags<T, COLL_TRT, V>(a, L, macros); break;
+        default: launch_vec_flags<T, COLL_MRT, V>(a, L, macros); break;
     }
 }
 
@@ -763,10 +759,13 @@ static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin,
         return LBM_OK;
     }
     a.row_count = row_count;
-    g_pdl = s->use_pdl && mode == MODE_STEP;
-    dim3 grid;
-    block_shape(s->cfg.nx, row_count, &g_block, &grid, s->cfg.batch);
-    if (grid.y > 65535u || grid.z > 65535u) {
+    const int vw = s->cfg.dtype == LBM_F64 ? s->vec_f64 : s->vec_f32;
+    const bool vec = mode == MODE_STEP && gather && vw > 1;
+    Launch L{};
+    L.st = st;
+    L.pdl = s->use_pdl && mode == MODE_STEP;
+    block_shape(vec ? (s->cfg.nx + vw - 1) / vw : s->cfg.nx, row_count, s->cfg.batch, &L);
+    if (L.grid.y > 65535u || L.grid.z > 65535u) {
         // split over rows in chunks the grid can express
         const int chunk = 65535;
         for (int off = 0; off < row_count; off += chunk) {
@@ -776,13 +775,12 @@ static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin,
         }
         return LBM_OK;
     }
-    const int vw = s->cfg.dtype == LBM_F64 ? s->vec_f64 : s->vec_f32;
-    if (mode == MODE_STEP && gather && vw > 1) {
-        if (s->cfg.dtype == LBM_F64) launch_vec_coll<double, 2>(s->cfg.collision, a, s->cfg.nx, row_count, s->cfg.batch, st, macros);
-        else if (vw == 4) launch_vec_coll<float, 4>(s->cfg.collision, a, s->cfg.nx, row_count, s->cfg.batch, st, macros);
-        else launch_vec_coll<float, 2>(s->cfg.collision, a, s->cfg.nx, row_count, s->cfg.batch, st, macros);
-    } else if (s->cfg.dtype == LBM_F64) dispatch_coll<double>(s->cfg.collision, a, grid, st, gather, macros, mode);
-    else dispatch_coll<float>(s->cfg.collision, a, grid, st, gather, macros, mode);
+    if (vec) {
+        if (s->cfg.dtype == LBM_F64) launch_vec_coll<double, 2>(s->cfg.collision, a, L, macros);
+        else if (vw == 4) launch_vec_coll<float, 4>(s->cfg.collision, a, L, macros);
+        else launch_vec_coll<float, 2>(s->cfg.collision, a, L, macros);
+    } else if (s->cfg.dtype == LBM_F64) dispatch_coll<double>(s->cfg.collision, a, L, gather, macros, mode);
+    else dispatch_coll<float>(s->cfg.collision, a, L, gather, macros, mode);
     s->launches++;
     CK(cudaGetLastError());
     return LBM_OK;

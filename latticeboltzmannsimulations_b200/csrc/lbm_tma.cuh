@@ -4,8 +4,8 @@
 // 2-D bulk-tensor loads (cp.async.bulk.tensor.2d), one per population.  The row shift of the pull step (y + c_ky)
 // is done by the copy engine's address generation (box origin row).  The column shift cannot be: measured on
 // B200, a box whose innermost coordinate is not 16-byte aligned raises "illegal instruction"
-// (tools/probes/tma_probe.cu), so populations with c_kx != 0 are fetched as a box one 16-byte vector wider
-// ([x0-V, x0+TX) for c_kx = +1, [x0, x0+TX+V) for c_kx = -1) and the one-element shift is applied when the compute
+// (tools/probes/tma_probe.cu), so populations with c_kx != 0 are fetched as a box one 128-byte line wider
+// ([x0-EXT, x0+TX) for c_kx = +1, [x0, x0+TX+EXT) for c_kx = -1) and the one-element shift is applied when the compute
 // warps read shared memory (two aligned 128-bit LDS + a compile-time select).  Boxes that hang over x < 0 or
 // x >= pitch are zero-filled by the hardware; rows never leave the buffer because every population plane carries a
 // ghost row above and below.  A STAGES-deep ring of {9 boxes, full mbarrier, empty
@@ -126,7 +126,10 @@ template <typename T, int V, int TY, int STAGES>
 struct TmaCfg {
     static constexpr int TXT = sizeof(T) == 8 ? 64 : 32;   // threads along x per tile row (box width TX+V <= 256)
     static constexpr int TX = TXT * V;             // nodes along x per tile
-    static constexpr int TXW = TX + V;             // columns of a wide box (one extra 16-byte vector)
+    static constexpr int EXT = 128 / sizeof(T);    // extra columns of a wide box: one full 128-byte line, so that every
+                                                   // box row starts and ends on a line boundary (16-byte-aligned but
+                                                   // line-misaligned rows ran the TMA path at a fraction of its rate)
+    static constexpr int TXW = TX + EXT;           // columns of a wide box
     static constexpr int CONSUMERS = TXT * TY;     // compute threads
     static constexpr int THREADS = CONSUMERS + 32; // + one producer warp
     static constexpr uint32_t NARROW_BYTES = TX * TY * sizeof(T);
@@ -181,7 +184,7 @@ lbm_step_tma(const __grid_constant__ CUtensorMap tmap_narrow, const __grid_const
                 for (int k = 0; k < 9; ++k) {
                     const int c1 = (b * 9 + k) * ts.rows_per_plane + row0 + lat_cy(k);
                     if (lat_cx(k) == 0) tma_load_2d(dst + Cfg::slot_off(k), &tmap_narrow, x0, c1, &full[stage]);
-                    else tma_load_2d(dst + Cfg::slot_off(k), &tmap_wide, lat_cx(k) > 0 ? x0 - V : x0, c1, &full[stage]);
+                    else tma_load_2d(dst + Cfg::slot_off(k), &tmap_wide, lat_cx(k) > 0 ? x0 - Cfg::EXT : x0, c1, &full[stage]);
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -215,9 +218,10 @@ lbm_step_tma(const __grid_constant__ CUtensorMap tmap_narrow, const __grid_const
 #pragma unroll
                     for (int v = 0; v < V; ++v) f[v][k] = tmp[v];
                 } else {
-                    // wide box: columns [x0-V, x0+TX) for c_x = +1, [x0, x0+TX+V) for c_x = -1; node x needs x - c_x
+                    // wide box: columns [x0-EXT, x0+TX) for c_x = +1, [x0, x0+TX+EXT) for c_x = -1; node x needs x - c_x
                     T lo[V], hi[V];
-                    const uint32_t row = st + Cfg::slot_off(k) + (uint32_t)((ty * Cfg::TXW + tx * V) * sizeof(T));
+                    const uint32_t row = st + Cfg::slot_off(k) +
+                                         (uint32_t)((ty * Cfg::TXW + tx * V + (lat_cx(k) > 0 ? Cfg::EXT - V : 0)) * sizeof(T));
                     lds_vec(row, lo);
                     lds_vec(row + 16, hi);
 #pragma unroll

@@ -386,3 +386,34 @@ def test_minimum_sizes(nx, ny):
     for dtype in ("float64", "float32"):
         got = L.run_cavity(nx, ny, 50, steps=25, dtype=dtype, return_f=True)
         assert_close(got, want, dtype, what="%dx%d" % (nx, ny))
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_tma_engine_parity(dtype):
+    """The optional TMA-staged persistent engine (cp.async.bulk.tensor ring) must give the same bits as the default
+    plain-load engine: the per-node arithmetic is shared, only the data movement differs."""
+    import latticeboltzmannsimulations_b200 as L
+    for (nx, ny, n) in ((300, 70, 45), (129, 33, 20)):
+        f0 = O.random_state(nx, ny, seed=4).astype(dtype)
+        ref = L.run_cavity(nx, ny, 1000, steps=n, dtype=dtype, f0=f0, return_f=True, engine="ldg")
+        got = L.run_cavity(nx, ny, 1000, steps=n, dtype=dtype, f0=f0, return_f=True, engine="tma")
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b)
+    with L.CavitySolver(64, 64, engine="tma") as s:
+        assert s.engine == "tma"
+
+
+@pytest.mark.parametrize("env", [{"LBM_B200_VEC_F64": "2", "LBM_B200_VEC_F32": "2"}, {"LBM_B200_VEC_F32": "1"},
+                                 {"LBM_B200_GRAPH": "0", "LBM_B200_PDL": "0"}])
+def test_kernel_variants_are_bit_identical(env, monkeypatch):
+    """Every compiled data-movement variant (scalar / 2 / 4 nodes per thread, with and without graphs and programmatic
+    dependent launch) produces the same bits as the default configuration."""
+    import latticeboltzmannsimulations_b200 as L
+    cases = [("float64", 200, 90, "MRT", False), ("float32", 131, 77, "SRT", False), ("float32", 96, 64, "MRT", True)]
+    ref = [L.run_cavity(nx, ny, 1000, steps=70, dtype=dt, collision=c, turb=t, return_f=True) for dt, nx, ny, c, t in cases]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for (dt, nx, ny, c, t), want in zip(cases, ref):
+        got = L.run_cavity(nx, ny, 1000, steps=70, dtype=dt, collision=c, turb=t, return_f=True)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), (env, dt, c)
