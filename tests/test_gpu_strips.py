@@ -79,3 +79,37 @@ def test_nccl_strips_under_torchrun():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "STRIPS_OK" in out.stdout
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_no_out_of_bounds_writes_canary(dtype):
+    """Caller-owned population buffers with sentinel guard zones before and after (compute-sanitizer is closed on
+    this pool): after stepping with every region / kernel form the guards and the pitch padding must be untouched."""
+    import torch
+    import latticeboltzmannsimulations_b200 as L
+    from latticeboltzmannsimulations_b200 import _capi
+    tdt = torch.float64 if dtype == "float64" else torch.float32
+    nx, ny, y0, nyl = 70, 40, 12, 17          # nx not a multiple of the vector width or 32; a strip in the middle
+    nbytes = L.CavitySolver.state_bytes(nx, ny, 1, dtype, ny_local=nyl)
+    n, guard, sentinel = nbytes // tdt.itemsize, 4096, -7.25
+    raw = [torch.full((n + 2 * guard,), sentinel, dtype=tdt, device="cuda") for _ in range(2)]
+    for r in raw:
+        r[guard:guard + n] = 0
+    with L.CavitySolver(nx, ny, 1, dtype, "MRT", y0=y0, ny_local=nyl,
+                        ext_buffers=[r[guard:].data_ptr() for r in raw]) as s:
+        s.set_reynolds(400)
+        s.init_equilibrium()
+        lay = s.layout
+        for it in range(6):
+            if it % 2:
+                s.step_region(_capi.LBM_REGION_EDGE); s.step_region(_capi.LBM_REGION_INTERIOR)
+            else:
+                s.step_region(_capi.LBM_REGION_ALL, write_macros=True)
+            s.swap()
+        s.download_f(); s.macros(current=True)
+        torch.cuda.synchronize()
+        for r in raw:
+            assert bool((r[:guard] == sentinel).all()) and bool((r[guard + n:] == sentinel).all())
+            body = r[guard:guard + n].view(9, int(lay.rows), int(lay.pitch))
+            assert bool((body[:, :, nx:] == 0).all())            # pitch padding never written
+            assert bool(torch.isfinite(body).all())
