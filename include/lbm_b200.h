@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LBM_B200_ABI_VERSION 1
+#define LBM_B200_ABI_VERSION 2
 
 enum lbm_status { LBM_OK = 0, LBM_EINVAL = 1, LBM_ECUDA = 2, LBM_ENOMEM = 3, LBM_ESTATE = 4 };
 enum lbm_dtype { LBM_F32 = 0, LBM_F64 = 1 };
@@ -35,6 +35,11 @@ enum lbm_dtype { LBM_F32 = 0, LBM_F64 = 1 };
 enum lbm_collision { LBM_SRT = 0, LBM_TRT = 1, LBM_MRT = 2 };
 /* which rows of the local strip a launch covers (multi-GPU overlap of halo exchange and interior) */
 enum lbm_region { LBM_REGION_ALL = 0, LBM_REGION_EDGE = 1, LBM_REGION_INTERIOR = 2 };
+/* which reference variant the step reproduces: C = MRT_GPU.py (push + NEBB in funBC; the product
+ * path), A = MRT.py (NumPy solver: SRT only, slice streaming with the exclusive xsize_max bound that leaves the
+ * last rows/columns stale, "= feq" left wall) -- a compatibility mode so that BASELINE config 1 can be compared on
+ * identical inputs; two simple passes per step, not tuned */
+enum lbm_semantics { LBM_SEMANTICS_C = 0, LBM_SEMANTICS_A = 1 };
 /* kernel family: plain coalesced loads, or TMA-staged persistent tiles */
 enum lbm_engine { LBM_ENGINE_AUTO = 0, LBM_ENGINE_LDG = 1, LBM_ENGINE_TMA = 2 };
 
@@ -52,6 +57,8 @@ typedef struct lbm_config {
     int32_t ny_local;     /* rows owned; 0 means the whole cavity (y0 must then be 0) */
     int32_t device;       /* CUDA device ordinal, -1 = current device */
     int32_t engine;       /* lbm_engine */
+    int32_t semantics;    /* lbm_semantics */
+    int32_t reserved;     /* must be 0 */
     void* ext_f[2];       /* optional caller-owned device buffers (e.g. torch tensors) for the A/B population
                              arrays, each lbm_state_bytes() long; NULL = the library allocates */
 } lbm_config_t;

@@ -19,6 +19,7 @@ LBM_ENGINE_AUTO, LBM_ENGINE_LDG, LBM_ENGINE_TMA = 0, 1, 2
 
 COLLISIONS = {"SRT": LBM_SRT, "TRT": LBM_TRT, "MRT": LBM_MRT}
 ENGINES = {"auto": LBM_ENGINE_AUTO, "ldg": LBM_ENGINE_LDG, "tma": LBM_ENGINE_TMA}
+SEMANTICS = {"C": 0, "A": 1}
 
 # every symbol include/lbm_b200.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = [
@@ -38,7 +39,8 @@ class LBMError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("batch", C.c_int32), ("dtype", C.c_int32),
                 ("collision", C.c_int32), ("turb", C.c_int32), ("y0", C.c_int32), ("ny_local", C.c_int32),
-                ("device", C.c_int32), ("engine", C.c_int32), ("ext_f", C.c_void_p * 2)]
+                ("device", C.c_int32), ("engine", C.c_int32), ("semantics", C.c_int32), ("reserved", C.c_int32),
+                ("ext_f", C.c_void_p * 2)]
 
 
 class Layout(C.Structure):

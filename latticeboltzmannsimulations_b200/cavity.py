@@ -17,14 +17,16 @@ from .solver import CavitySolver
 
 def run_cavity(nx: int, ny: int, Re: float, uLB: float = 0.08, steps: int = 1000, collision: str = "MRT",
                dtype="float64", turb: bool = False, f0=None, return_f: bool = False, current_macros: bool = False,
-               device: Optional[int] = None, engine: str = "auto"):
+               device: Optional[int] = None, engine: str = "auto", semantics: str = "C"):
     """One lid-driven cavity: returns ``(rho[nx,ny], u[2,nx,ny])`` (+ ``f[9,nx,ny]`` with ``return_f``).
 
     ``rho, u`` carry the reference's one-step lag (they are the moments of the state that entered the last step);
     pass ``current_macros=True`` for the moments of the returned ``f`` instead.  ``f0`` (``[9,nx,ny]``, host array,
     e.g. pinned) replaces the equilibrium start ``rho = 1, u = (uLB,0)`` on the lid row (``MRT_GPU.py:259-267``).
+    ``semantics="A"`` (with ``collision="SRT"``) reproduces the NumPy solver ``MRT.py:286-453`` instead of the GPU
+    scripts, quirks included, for like-for-like comparisons with that script.
     """
-    with CavitySolver(nx, ny, 1, dtype, collision, turb, device=device, engine=engine) as s:
+    with CavitySolver(nx, ny, 1, dtype, collision, turb, device=device, engine=engine, semantics=semantics) as s:
         s.set_reynolds(Re, uLB)
         if f0 is None:
             s.init_equilibrium()

@@ -296,6 +296,89 @@ __global__ void __launch_bounds__(256) lbm_step_vec(const StepArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Semantics "A" (MRT.py:286-453), compatibility mode: two plain passes per step on pre-collision `fin`.
+//   pass 1  moments + overrides (:292-342), SRT collision (:396)            fin -> fpost, rho, u
+//   pass 2  slice streaming with xsize_max / ysize_max as EXCLUSIVE bounds (:404-414): slots outside the slices keep
+//           their old value; then the four wall assignments in the script's order (:450-453), left wall "= feq"
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void lbm_A_collide(const StepArgs a) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.nx) return;
+    const int y = blockIdx.y, b = blockIdx.z;
+    const T* __restrict__ fin = static_cast<const T*>(a.src) + (long long)b * a.cavity;
+    T* __restrict__ fpost = static_cast<T*>(a.dst) + (long long)b * a.cavity;
+    const long long rc = (long long)(y + 1) * a.pitch + x;
+    const Rates<T> r(a.cav[b]);
+    T f[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f[k] = fin[k * a.plane + rc];
+    T rho, jx, jy;
+    moments_ref<T>(f, rho, jx, jy);
+    T ux = jx / rho, uy = jy / rho;
+    if (y == 0) rho = rho_lid_formula<T>(f);                              // MRT.py:337
+    if (x == 0 || x == a.nx - 1 || y == a.ny - 1) { ux = (T)0; uy = (T)0; }   // :341
+    if (y == 0) { ux = r.uLB; uy = (T)0; }                                // :342
+    collide_srt<T>(f, rho, ux, uy, r.omega);                              // :396
+#pragma unroll
+    for (int k = 0; k < 9; ++k) fpost[k * a.plane + rc] = f[k];
+    const long long m = (long long)b * a.mplane + (long long)y * a.pitch + x;
+    static_cast<T*>(a.rho)[m] = rho;
+    static_cast<T*>(a.ux)[m] = ux;
+    static_cast<T*>(a.uy)[m] = uy;
+}
+
+template <typename T>
+__global__ void lbm_A_stream_bc(const StepArgs a) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.nx) return;
+    const int y = blockIdx.y, b = blockIdx.z;
+    const int nx = a.nx, ny = a.ny;
+    const T* __restrict__ fpost = static_cast<const T*>(a.src) + (long long)b * a.cavity;
+    T* __restrict__ fin = static_cast<T*>(a.dst) + (long long)b * a.cavity;
+    const long long P = a.plane;
+    const long long rc = (long long)(y + 1) * a.pitch + x, ru = rc - a.pitch, rd = rc + a.pitch;
+    // target ranges of the slice assignments MRT.py:404-414
+    const bool xr = x >= 1 && x <= nx - 2;       // c_x = +1 : fin[k, 1:xm]     <- fpost[k, 0:xm-1]
+    const bool xl = x <= nx - 3;                 // c_x = -1 : fin[k, 0:xm-1]   <- fpost[k, 1:xm]
+    const bool yu = y <= ny - 3;                 // c_y = +1 : fin[k, :, 0:ym-1] <- fpost[k, :, 1:ym]
+    const bool yd = y >= 1 && y <= ny - 2;       // c_y = -1 : fin[k, :, 1:ym]   <- fpost[k, :, 0:ym-1]
+    T f[9];
+    f[0] = fpost[rc];
+    f[1] = xr ? fpost[1 * P + rc - 1] : fin[1 * P + rc];
+    f[2] = yu ? fpost[2 * P + rd] : fin[2 * P + rc];
+    f[3] = xl ? fpost[3 * P + rc + 1] : fin[3 * P + rc];
+    f[4] = yd ? fpost[4 * P + ru] : fin[4 * P + rc];
+    f[5] = (xr && yu) ? fpost[5 * P + rd - 1] : fin[5 * P + rc];
+    f[6] = (xl && yu) ? fpost[6 * P + rd + 1] : fin[6 * P + rc];
+    f[7] = (xl && yd) ? fpost[7 * P + ru + 1] : fin[7 * P + rc];
+    f[8] = (xr && yd) ? fpost[8 * P + ru - 1] : fin[8 * P + rc];
+    if (x == 0 || x == nx - 1 || y == 0 || y == ny - 1) {
+        const long long m = (long long)b * a.mplane + (long long)y * a.pitch + x;
+        T fe[9];
+        feq_all<T>(static_cast<const T*>(a.rho)[m], static_cast<const T*>(a.ux)[m], static_cast<const T*>(a.uy)[m], fe);
+        if (x == 0) { f[1] = fe[1]; f[5] = fe[5]; f[8] = fe[8]; }                         // :450
+        if (x == nx - 1) {                                                                // :451  (3,6,7) <- (1,5,8)
+            f[3] = -fe[1] + (fe[3] + f[1]);
+            f[6] = -fe[5] + (fe[6] + f[5]);
+            f[7] = -fe[8] + (fe[7] + f[8]);
+        }
+        if (y == ny - 1) {                                                                // :452  (2,5,6) <- (4,7,8)
+            f[2] = -fe[4] + (fe[2] + f[4]);
+            f[5] = -fe[7] + (fe[5] + f[7]);
+            f[6] = -fe[8] + (fe[6] + f[8]);
+        }
+        if (y == 0) {                                                                     // :453  (4,7,8) <- (2,5,6)
+            f[4] = -fe[2] + (fe[4] + f[2]);
+            f[7] = -fe[5] + (fe[7] + f[5]);
+            f[8] = -fe[6] + (fe[8] + f[6]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) fin[k * P + rc] = f[k];
+}
+
 // Equilibrium start (MRT_GPU.py:259-267): rho = 1, u = (uLB, 0) on row y == 0, evaluated in fp64 then cast
 // (the reference builds it in fp64 NumPy and casts to fp32, :298).  Also seeds the corner carries and rho = 1, u = 0.
 template <typename T>
@@ -829,6 +912,13 @@ static int check_cfg(const lbm_config_t* c, int* nyl_out) {
     if (c->ny_local == 0 && c->y0 != 0) return fail(LBM_EINVAL, "y0 must be 0 when ny_local == 0");
     if (c->y0 < 0 || nyl < 1 || c->y0 + nyl > c->ny) return fail(LBM_EINVAL, "y-strip [y0, y0+ny_local) outside [0, ny)");
     if (c->engine < LBM_ENGINE_AUTO || c->engine > LBM_ENGINE_TMA) return fail(LBM_EINVAL, "bad engine");
+    if (c->semantics != LBM_SEMANTICS_C && c->semantics != LBM_SEMANTICS_A) return fail(LBM_EINVAL, "bad semantics");
+    if (c->reserved != 0) return fail(LBM_EINVAL, "reserved must be 0");
+    if (c->semantics == LBM_SEMANTICS_A) {
+        if (c->collision != LBM_SRT || c->turb) return fail(LBM_EINVAL, "semantics A (MRT.py) is SRT without turbulence model");
+        if (nyl != c->ny) return fail(LBM_EINVAL, "semantics A does not support y-strips");
+        if (c->ny > 65535) return fail(LBM_EINVAL, "semantics A supports ny <= 65535");
+    }
     *nyl_out = nyl;
     return LBM_OK;
 }
@@ -1117,8 +1207,22 @@ int lbm_download_f(lbm_handle_t s, void* f, int on_device, void* stream) {
     return move_planes(s, f, fcav, on_device != 0, false, s->cfg.batch, 9, fin, s->plane, s->cavity, s->pitch, st);
 }
 
+// One step of semantics A: collide (f[0] -> f[1], rho, u), then stream + walls (f[1], f[0] -> f[0] in place).
+static int step_A(lbm_solver* s, cudaStream_t st) {
+    dim3 grid((s->cfg.nx + 255) / 256, s->cfg.ny, s->cfg.batch);
+    StepArgs a = make_args(s, s->f[0], s->f[1]);
+    StepArgs b = make_args(s, s->f[1], s->f[0]);
+    if (s->esz == 8) { lbm_A_collide<double><<<grid, 256, 0, st>>>(a); lbm_A_stream_bc<double><<<grid, 256, 0, st>>>(b); }
+    else { lbm_A_collide<float><<<grid, 256, 0, st>>>(a); lbm_A_stream_bc<float><<<grid, 256, 0, st>>>(b); }
+    s->launches += 2;
+    CK(cudaGetLastError());
+    s->steps++;
+    return LBM_OK;
+}
+
 int lbm_step_region(lbm_handle_t s, int region, int write_macros, void* stream) {
     if (!s) return fail(LBM_EINVAL, "NULL handle");
+    if (s->cfg.semantics == LBM_SEMANTICS_A) return fail(LBM_ESTATE, "semantics A has no region stepping: use lbm_step");
     int rc = set_device(s);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1137,6 +1241,7 @@ int lbm_step_region(lbm_handle_t s, int region, int write_macros, void* stream) 
 
 int lbm_swap(lbm_handle_t s) {
     if (!s) return fail(LBM_EINVAL, "NULL handle");
+    if (s->cfg.semantics == LBM_SEMANTICS_A) return fail(LBM_ESTATE, "semantics A has no region stepping: use lbm_step");
     s->cur ^= 1; s->pre = false; s->steps++;
     return LBM_OK;
 }
@@ -1178,6 +1283,14 @@ int lbm_step(lbm_handle_t s, int nsteps, int write_macros, void* stream) {
     if (nsteps < 0) return fail(LBM_EINVAL, "nsteps < 0");
     if (s->nyl != s->cfg.ny && nsteps > 1)
         return fail(LBM_ESTATE, "a y-strip handle needs a halo exchange between steps: use lbm_step_region/lbm_swap");
+    if (s->cfg.semantics == LBM_SEMANTICS_A) {
+        int rc = set_device(s);
+        if (rc) return rc;
+        rc = sync_params(s, (cudaStream_t)stream);
+        if (rc) return rc;
+        for (int i = 0; i < nsteps; ++i) { rc = step_A(s, (cudaStream_t)stream); if (rc) return rc; }
+        return LBM_OK;
+    }
     int left = nsteps;
     const bool small = (long long)s->cfg.nx * s->nyl * s->cfg.batch <= LBM_GRAPH_MAX_NODES;
     while (left > 0) {

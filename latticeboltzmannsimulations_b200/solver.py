@@ -31,7 +31,7 @@ def _is_torch_cuda(x) -> bool:
 class CavitySolver:
     def __init__(self, nx: int, ny: int, batch: int = 1, dtype="float64", collision: str = "MRT",
                  turb: bool = False, y0: int = 0, ny_local: Optional[int] = None, device: Optional[int] = None,
-                 engine: str = "auto", ext_buffers: Optional[Sequence[int]] = None):
+                 engine: str = "auto", ext_buffers: Optional[Sequence[int]] = None, semantics: str = "C"):
         self._lib = _capi.load()
         self._h = C.c_void_p()
         self.nx, self.ny, self.batch = int(nx), int(ny), int(batch)
@@ -41,13 +41,17 @@ class CavitySolver:
             raise ValueError("collision must be one of %s" % sorted(_capi.COLLISIONS))
         if engine not in _capi.ENGINES:
             raise ValueError("engine must be one of %s" % sorted(_capi.ENGINES))
+        if semantics not in _capi.SEMANTICS:
+            raise ValueError("semantics must be 'C' (MRT_GPU.py) or 'A' (MRT.py)")
         self.collision = collision
+        self.semantics = semantics
         self.y0 = int(y0)
         self.ny_local = int(ny) if ny_local is None else int(ny_local)
         cfg = _capi.Config(nx=self.nx, ny=self.ny, batch=self.batch, dtype=code,
                            collision=_capi.COLLISIONS[collision], turb=int(bool(turb)), y0=self.y0,
                            ny_local=0 if ny_local is None else self.ny_local,
-                           device=-1 if device is None else int(device), engine=_capi.ENGINES[engine])
+                           device=-1 if device is None else int(device), engine=_capi.ENGINES[engine],
+                           semantics=_capi.SEMANTICS[semantics], reserved=0)
         if ext_buffers is not None:
             cfg.ext_f[0], cfg.ext_f[1] = int(ext_buffers[0]), int(ext_buffers[1])
         self._cfg = cfg
@@ -79,7 +83,7 @@ class CavitySolver:
         lib = _capi.load()
         code, _ = _DTYPES[_dtype_name(dtype)]
         cfg = _capi.Config(nx=nx, ny=ny, batch=batch, dtype=code, collision=_capi.LBM_MRT, turb=0, y0=0,
-                           ny_local=0 if ny_local is None else ny_local, device=-1, engine=0)
+                           ny_local=0 if ny_local is None else ny_local, device=-1, engine=0, semantics=0, reserved=0)
         out = C.c_size_t()
         _capi.check(lib.lbm_state_bytes(C.byref(cfg), C.byref(out)))
         return int(out.value)

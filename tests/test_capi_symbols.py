@@ -24,19 +24,20 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_capi.SYMBOLS) == names
-    assert lib.lbm_abi_version() == 1
+    assert lib.lbm_abi_version() == 2
 
 
 def test_config_struct_matches_header_size():
     from latticeboltzmannsimulations_b200 import _capi
-    assert ctypes.sizeof(_capi.Config) == 10 * 4 + 2 * 8
+    assert ctypes.sizeof(_capi.Config) == 12 * 4 + 2 * 8
     assert ctypes.sizeof(_capi.Layout) == 6 * 8
 
 
 def test_argument_validation_without_gpu():
     from latticeboltzmannsimulations_b200 import _capi
     lib = _capi.load()
-    cfg = _capi.Config(nx=2, ny=64, batch=1, dtype=1, collision=2, turb=0, y0=0, ny_local=0, device=-1, engine=0)
+    cfg = _capi.Config(nx=2, ny=64, batch=1, dtype=1, collision=2, turb=0, y0=0, ny_local=0, device=-1, engine=0,
+                       semantics=0, reserved=0)
     n = ctypes.c_size_t()
     assert lib.lbm_state_bytes(ctypes.byref(cfg), ctypes.byref(n)) == _capi.LBM_EINVAL
     assert b"nx" in lib.lbm_last_error()

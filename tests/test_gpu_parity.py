@@ -141,6 +141,10 @@ def test_ghia_re100_128():
     rho32, u32 = L.run_cavity(128, 128, 100, 0.08, steps=40000, collision="MRT", dtype="float32")
     ex32, ey32 = O.ghia_errors(u32.astype(np.float64), 0.08, O.load_ghia())
     assert ex32 < 0.015 and ey32 < 0.015, (ex32, ey32)
+    # the literal config 1: semantics A (MRT.py), SRT; SURVEY.md 0-2 expects 0.0205 / 0.0386 for the reference itself
+    rhoA, uA = L.run_cavity(128, 128, 100, 0.08, steps=40000, collision="SRT", dtype="float64", semantics="A")
+    exA, eyA = O.ghia_errors(uA, 0.08, O.load_ghia())
+    assert exA < 0.03 and eyA < 0.05, (exA, eyA)
 
 
 def test_batch_equals_standalone():
@@ -417,3 +421,32 @@ def test_kernel_variants_are_bit_identical(env, monkeypatch):
         got = L.run_cavity(nx, ny, 1000, steps=70, dtype=dt, collision=c, turb=t, return_f=True)
         for a, b in zip(got, want):
             assert np.array_equal(a, b), (env, dt, c)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("name", ["ref_A_32x32_Re100_N25.npz", "ref_A_40x24_Re400_N60.npz"])
+def test_semantics_A_against_the_real_MRT_py(name, dtype):
+    """Compatibility mode semantics='A' against outputs of the REAL reference script MRT.py (goldens written by
+    executing /root/reference/MRT.py, tests/golden/make_golden.py) -- BASELINE config 1 on identical inputs."""
+    import latticeboltzmannsimulations_b200 as L
+    d, nx, ny, Re, n, uLB = _golden(name)
+    got = L.run_cavity(nx, ny, Re, uLB, steps=n, collision="SRT", dtype=dtype, semantics="A", return_f=True)
+    assert_close(got, (d["rho"], d["u"], d["fin"]), dtype, uLB, name)
+
+
+def test_semantics_A_config1_128_and_quirks():
+    """Config 1 shape (128x128, Re 100) for 2000 steps against oracle A, from a random state too; the stale
+    rows/columns of MRT.py's slice streaming keep their initial values exactly."""
+    import latticeboltzmannsimulations_b200 as L
+    nx = ny = 128
+    p = O.Params(nx, ny, Re=100, collision="SRT")
+    for f0 in (None, O.random_state(nx, ny, seed=8)):
+        want = O.run(p, 300, semantics="A", fin0=f0)
+        got = L.run_cavity(nx, ny, 100, steps=300, collision="SRT", semantics="A", f0=f0, return_f=True)
+        assert_close(got, want, "float64", what="A 128")
+        init = O.init_fields(nx, ny, 0.08)[2] if f0 is None else f0
+        f = got[2]
+        assert np.array_equal(f[3, nx - 2, 1:-1], init[3, nx - 2, 1:-1])       # k=3 at x = nx-2 is never written
+        assert np.array_equal(f[2, 1:-1, ny - 2], init[2, 1:-1, ny - 2])       # k=2 at y = ny-2 is never written
+    with pytest.raises(L.LBMError, match="semantics A"):
+        L.CavitySolver(32, 32, collision="MRT", semantics="A")
