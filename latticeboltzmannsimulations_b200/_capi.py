@@ -56,14 +56,19 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("LBM_B200_LIB", LIB_PATH)        # development override (experimental builds)
+    if path != LIB_PATH:
+        lib = C.CDLL(path)
+    elif not os.path.exists(LIB_PATH):
         try:
             from . import build as _build
             _build.build()
         except Exception as exc:  # pragma: no cover - build container always has nvcc
             raise ImportError("liblbm_b200.so is not built and could not be built (%s); run "
                               "`python -m latticeboltzmannsimulations_b200.build`. There is no CPU fallback." % exc)
-    lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+    else:
+        lib = C.CDLL(LIB_PATH)
     H = C.c_void_p
     lib.lbm_last_error.restype = C.c_char_p
     lib.lbm_last_error.argtypes = []

@@ -39,6 +39,31 @@ static int fail(int code, const std::string& msg) {
                         std::string(#call) + ": " + cudaGetErrorString(e__));                            \
     } while (0)
 
+// Cache-policy experiment hooks (compile with -DLBM_CACHE_HINTS=n; the shipped build uses 0 = default policy).
+#ifndef LBM_CACHE_HINTS
+#define LBM_CACHE_HINTS 0
+#endif
+template <typename T> __device__ __forceinline__ T ld_pop(const T* p) {
+#if LBM_CACHE_HINTS == 2
+    return __ldcs(p);
+#elif LBM_CACHE_HINTS == 3
+    return __ldg(p);
+#elif LBM_CACHE_HINTS == 4
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+template <typename T> __device__ __forceinline__ void st_pop(T* p, T v) {
+#if LBM_CACHE_HINTS == 1 || LBM_CACHE_HINTS == 2
+    __stcs(p, v);
+#elif LBM_CACHE_HINTS == 4
+    __stcg(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // "ldg" family: one thread per node, plain coalesced loads (x+-1 shifted reads are unaligned-but-contiguous per
 // warp and are absorbed by L1/L2), aligned stores.  Template flags: dtype, collision, GATHER (false for the first
@@ -69,15 +94,15 @@ __global__ void __launch_bounds__(256) lbm_step_ldg(const StepArgs a) {
     T f[9];
     if (GATHER) {
         // pull: f_k arrives from (x - c_kx, y + c_ky)
-        f[0] = src[rc];
-        f[1] = left ? (T)0 : src[1 * P + rc - 1];
-        f[2] = bot ? (T)0 : src[2 * P + rd];
-        f[3] = right ? (T)0 : src[3 * P + rc + 1];
-        f[4] = lid ? (T)0 : src[4 * P + ru];
-        f[5] = (left || bot) ? (T)0 : src[5 * P + rd - 1];
-        f[6] = (right || bot) ? (T)0 : src[6 * P + rd + 1];
-        f[7] = (right || lid) ? (T)0 : src[7 * P + ru + 1];
-        f[8] = (left || lid) ? (T)0 : src[8 * P + ru - 1];
+        f[0] = ld_pop(src + rc);
+        f[1] = left ? (T)0 : ld_pop(src + 1 * P + rc - 1);
+        f[2] = bot ? (T)0 : ld_pop(src + 2 * P + rd);
+        f[3] = right ? (T)0 : ld_pop(src + 3 * P + rc + 1);
+        f[4] = lid ? (T)0 : ld_pop(src + 4 * P + ru);
+        f[5] = (left || bot) ? (T)0 : ld_pop(src + 5 * P + rd - 1);
+        f[6] = (right || bot) ? (T)0 : ld_pop(src + 6 * P + rd + 1);
+        f[7] = (right || lid) ? (T)0 : ld_pop(src + 7 * P + ru + 1);
+        f[8] = (left || lid) ? (T)0 : ld_pop(src + 8 * P + ru - 1);
         if (left || right || lid || bot) {
             const int slot = corner_slot(left, right, lid, bot);
             T* carry = static_cast<T*>(a.carry) + b * 4;
@@ -120,7 +145,7 @@ __global__ void __launch_bounds__(256) lbm_step_ldg(const StepArgs a) {
         }
         if (lid) static_cast<T*>(a.rho_lid)[(long long)b * a.pitch + x] = rho;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) dst[k * P + rc] = f[k];
+        for (int k = 0; k < 9; ++k) st_pop(dst + k * P + rc, f[k]);
     }
     if (MACROS || MODE == MODE_MACROS) {
         const long long m = (long long)b * a.mplane + (long long)yl * a.pitch + x;
