@@ -322,6 +322,116 @@ __global__ void __launch_bounds__(256) lbm_step_vec(const StepArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Temporal blocking: TWO lattice steps per pass over memory.  A CTA owns a TX x TY tile.  Sub-step 1 advances the
+// tile grown by one node on every side (pulling, like the scalar kernel, from the global post-collision buffer,
+// wall rule on read) and keeps the resulting post-collision populations in shared memory; after one barrier,
+// sub-step 2 advances the tile itself by pulling from shared memory and stores to the other global buffer.  Per
+// node and TWO steps the kernel moves 9 loads (+ the tile halo, served by L2) and 9 stores: half the DRAM traffic
+// per update of the one-step kernels, at the price of recomputing the one-node ring ((TX+2)(TY+2)/(TX TY) - 1 of
+// sub-step 1) -- the step is HBM-bound with the fp64 pipe 24 % busy, so the arithmetic is available.
+// The per-node arithmetic is the shared node_update()/wall_rule(), so results are bit-identical to two one-step
+// launches.  The lid density and corner carries of the intermediate state live in shared memory; those of the
+// final state go to the other half of the double-buffered side arrays (a neighbouring CTA may still need the old
+// ones for its halo ring).  Whole cavities only (a y-strip would need a two-row halo exchange).
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, int TX_, int TY_> struct Fused2Cfg {
+    static constexpr int TX = TX_, TY = TY_;
+    static constexpr int RX = TX + 2, RY = TY + 2;                 // tile grown by one node
+    static constexpr int PLANE = RX * RY;
+    static constexpr size_t SMEM = (size_t)(9 * PLANE + RX + 4) * sizeof(T);
+};
+
+template <typename T, int COLL, bool MACROS, int TX_, int TY_, int MINB>
+__global__ void __launch_bounds__(256, MINB) lbm_step_fused2(const StepArgs a) {
+    using Cfg = Fused2Cfg<T, TX_, TY_>;
+    extern __shared__ __align__(16) unsigned char fused_smem[];
+    T* h1 = reinterpret_cast<T*>(fused_smem);                      // [9][RY][RX] post-collision after sub-step 1
+    T* rl1 = h1 + 9 * Cfg::PLANE;                                  // [RX] lid density after sub-step 1
+    T* c1 = rl1 + Cfg::RX;                                         // [4]  corner carries after sub-step 1
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * Cfg::TX, y0 = blockIdx.y * Cfg::TY;   // tile origin (whole cavity: local row == y)
+    const T* __restrict__ src = static_cast<const T*>(a.src) + (long long)b * a.cavity;
+    T* __restrict__ dst = static_cast<T*>(a.dst) + (long long)b * a.cavity;
+    const long long P = a.plane;
+    const Rates<T> r(a.cav[b]);
+    const T* carry_in = static_cast<const T*>(a.carry) + b * 4;
+    const T* rl_in = static_cast<const T*>(a.rho_lid) + (long long)b * a.pitch;
+
+    // ---- sub-step 1 on the grown tile: global (state t) -> shared (state t+1) ----
+    for (int i = threadIdx.x; i < Cfg::PLANE; i += blockDim.x) {
+        const int ly = i / Cfg::RX, lx = i - ly * Cfg::RX;
+        const int x = x0 - 1 + lx, y = y0 - 1 + ly;
+        if (x < 0 || x >= a.nx || y < 0 || y >= a.ny) continue;
+        const bool left = (x == 0), right = (x == a.nx - 1), lid = (y == 0), bot = (y == a.ny - 1);
+        const long long rc = (long long)(y + 1) * a.pitch + x, ru = rc - a.pitch, rd = rc + a.pitch;
+        T f[9];
+        f[0] = src[rc];
+        f[1] = left ? (T)0 : src[1 * P + rc - 1];
+        f[2] = bot ? (T)0 : src[2 * P + rd];
+        f[3] = right ? (T)0 : src[3 * P + rc + 1];
+        f[4] = lid ? (T)0 : src[4 * P + ru];
+        f[5] = (left || bot) ? (T)0 : src[5 * P + rd - 1];
+        f[6] = (right || bot) ? (T)0 : src[6 * P + rd + 1];
+        f[7] = (right || lid) ? (T)0 : src[7 * P + ru + 1];
+        f[8] = (left || lid) ? (T)0 : src[8 * P + ru - 1];
+        if (left || right || lid || bot) {
+            const int slot = corner_slot(left, right, lid, bot);
+            const T stale = slot >= 0 ? carry_in[slot] : (T)0;
+            const T rl = lid ? rl_in[x] : (T)1;
+            wall_rule<T>(f, left, right, lid, bot, rl, r.uLB, stale);
+            if (slot >= 0) c1[slot] = corner_value<T>(f, slot);
+        }
+        T rho, ux, uy;
+        node_update<T, COLL, false>(f, r, left, right, lid, bot, rho, ux, uy);
+        if (lid) rl1[lx] = rho;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) h1[k * Cfg::PLANE + i] = f[k];
+    }
+    __syncthreads();
+
+    // ---- sub-step 2 on the tile: shared (state t+1) -> global (state t+2) ----
+    for (int i = threadIdx.x; i < Cfg::TX * Cfg::TY; i += blockDim.x) {
+        const int ty = i / Cfg::TX, tx = i - ty * Cfg::TX;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x >= a.nx || y >= a.ny) continue;
+        const bool left = (x == 0), right = (x == a.nx - 1), lid = (y == 0), bot = (y == a.ny - 1);
+        const int c = (ty + 1) * Cfg::RX + (tx + 1);               // this node inside the grown tile
+        const int u = c - Cfg::RX, d = c + Cfg::RX;                // row y-1 / y+1
+        T f[9];
+        f[0] = h1[c];
+        f[1] = left ? (T)0 : h1[1 * Cfg::PLANE + c - 1];
+        f[2] = bot ? (T)0 : h1[2 * Cfg::PLANE + d];
+        f[3] = right ? (T)0 : h1[3 * Cfg::PLANE + c + 1];
+        f[4] = lid ? (T)0 : h1[4 * Cfg::PLANE + u];
+        f[5] = (left || bot) ? (T)0 : h1[5 * Cfg::PLANE + d - 1];
+        f[6] = (right || bot) ? (T)0 : h1[6 * Cfg::PLANE + d + 1];
+        f[7] = (right || lid) ? (T)0 : h1[7 * Cfg::PLANE + u + 1];
+        f[8] = (left || lid) ? (T)0 : h1[8 * Cfg::PLANE + u - 1];
+        if (left || right || lid || bot) {
+            const int slot = corner_slot(left, right, lid, bot);
+            const T stale = slot >= 0 ? c1[slot] : (T)0;
+            const T rl = lid ? rl1[tx + 1] : (T)1;
+            wall_rule<T>(f, left, right, lid, bot, rl, r.uLB, stale);
+            if (slot >= 0) static_cast<T*>(a.carry_out)[b * 4 + slot] = corner_value<T>(f, slot);
+        }
+        T rho, ux, uy;
+        node_update<T, COLL, MACROS>(f, r, left, right, lid, bot, rho, ux, uy);
+        if (lid) static_cast<T*>(a.rho_lid_out)[(long long)b * a.pitch + x] = rho;
+        const long long rc = (long long)(y + 1) * a.pitch + x;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dst[k * P + rc] = f[k];
+        if (MACROS) {
+            const long long m = (long long)b * a.mplane + (long long)y * a.pitch + x;
+            static_cast<T*>(a.rho)[m] = rho;
+            static_cast<T*>(a.ux)[m] = ux;
+            static_cast<T*>(a.uy)[m] = uy;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Semantics "A" (MRT.py:286-453), compatibility mode: two plain passes per step on pre-collision `fin`.
 //   pass 1  moments + overrides (:292-342), SRT collision (:396)            fin -> fpost, rho, u
 //   pass 2  slice streaming with xsize_max / ysize_max as EXCLUSIVE bounds (:404-414): slots outside the slices keep
@@ -626,10 +736,13 @@ struct lbm_solver {
     // fp64 scalar 47 067 vs vec2 45 905 MLUPS; fp32 scalar 87 132, vec2 88 321, vec4 91 055 MLUPS.
     int vec_f64 = 1, vec_f32 = 4;
     // CUDA graphs of the steady step loop: graph[p] = 2*GRAPH_PAIRS launches starting with buffer p as source
-    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};   // index = cur * 2 + side
     cudaStream_t capture_stream = nullptr;
     int use_graph = 1;
     int use_pdl = 1;
+    int use_fused2 = 1;        // temporal blocking (two steps per launch) for whole cavities
+    int side = 0;              // which half of the double-buffered rho_lid / carry arrays is current
+    int fused2_tile = -1;      // tile-shape variant of the fused kernel (-1 = per-dtype default)
 };
 
 // A fresh state (init / upload) un-freezes every cavity; graphs captured with the old flag pointer are dropped.
@@ -637,7 +750,7 @@ static void reset_active(lbm_solver* s) {
     if (!s->active) return;
     cudaFree(s->active);
     s->active = nullptr;
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 4; ++i)
         if (s->graph[i]) { cudaGraphExecDestroy(s->graph[i]); s->graph[i] = nullptr; }
 }
 
@@ -650,7 +763,12 @@ static StepArgs make_args(lbm_solver* s, const void* src, void* dst) {
     StepArgs a{};
     a.src = src; a.dst = dst;
     a.rho = s->rho; a.ux = s->ux; a.uy = s->uy;
-    a.rho_lid = s->rho_lid; a.carry = s->carry; a.cav = s->cav;
+    const size_t rl_half = (size_t)s->cfg.batch * s->pitch * s->esz, ca_half = (size_t)s->cfg.batch * 4 * s->esz;
+    a.rho_lid = (char*)s->rho_lid + s->side * rl_half;
+    a.carry = (char*)s->carry + s->side * ca_half;
+    a.rho_lid_out = (char*)s->rho_lid + (s->side ^ 1) * rl_half;
+    a.carry_out = (char*)s->carry + (s->side ^ 1) * ca_half;
+    a.cav = s->cav;
     a.pi_eq = s->pi_eq; a.rho_prev = s->rho_prev;
     a.active = s->active;
     a.nx = s->cfg.nx; a.ny = s->cfg.ny; a.y0 = s->cfg.y0; a.nyl = s->nyl; a.pitch = s->pitch;
@@ -849,6 +967,63 @@ static void launch_vec_coll(int coll, const StepArgs& a, const Launch& L, bool m
     }
 }
 
+// ---- fused two-step launch ------------------------------------------------------------------------------------
+template <typename T, int COLL, int TX, int TY, int MINB>
+static cudaError_t launch_fused2_tile(lbm_solver* s, const StepArgs& a, bool macros, cudaStream_t st) {
+    using Cfg = Fused2Cfg<T, TX, TY>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(lbm_step_fused2<T, COLL, false, TX, TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(lbm_step_fused2<T, COLL, true, TX, TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((s->cfg.nx + Cfg::TX - 1) / Cfg::TX, (s->cfg.ny + Cfg::TY - 1) / Cfg::TY, s->cfg.batch);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(256, 1, 1); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = s->use_pdl ? 1 : 0;
+    if (macros) return cudaLaunchKernelEx(&cfg, lbm_step_fused2<T, COLL, true, TX, TY, MINB>, a);
+    return cudaLaunchKernelEx(&cfg, lbm_step_fused2<T, COLL, false, TX, TY, MINB>, a);
+}
+
+template <typename T, int COLL>
+static cudaError_t launch_fused2_t(lbm_solver* s, const StepArgs& a, bool macros, cudaStream_t st) {
+    // defaults from tools/fused2_sweep.py at 4096^2: fp64 64x8 tiles at 4 CTAs/SM (73 610 MLUPS), fp32 32x16 at 4 CTAs/SM (105 000-113 000)
+    const int variant = s->fused2_tile >= 0 ? s->fused2_tile : (sizeof(T) == 8 ? 3 : 4);
+    switch (variant) {
+        case 1: return launch_fused2_tile<T, COLL, 64, 8, 3>(s, a, macros, st);
+        case 2: return launch_fused2_tile<T, COLL, 32, 16, 3>(s, a, macros, st);
+        case 3: return launch_fused2_tile<T, COLL, 64, 8, 4>(s, a, macros, st);
+        case 4: return launch_fused2_tile<T, COLL, 32, 16, 4>(s, a, macros, st);
+        case 5: return launch_fused2_tile<T, COLL, 64, 12, 3>(s, a, macros, st);
+        case 6: return launch_fused2_tile<T, COLL, 32, 16, 5>(s, a, macros, st);
+        case 7: return launch_fused2_tile<T, COLL, 32, 8, 6>(s, a, macros, st);
+        default: return launch_fused2_tile<T, COLL, 64, 16, 2>(s, a, macros, st);
+    }
+}
+
+// Two steps in one launch: cur -> cur^1, side -> side^1.
+static int launch_fused2(lbm_solver* s, bool macros, cudaStream_t st) {
+    StepArgs a = make_args(s, s->f[s->cur], s->f[s->cur ^ 1]);
+    cudaError_t e;
+    if (s->cfg.dtype == LBM_F64) {
+        e = s->cfg.collision == LBM_SRT ? launch_fused2_t<double, COLL_SRT>(s, a, macros, st)
+          : s->cfg.collision == LBM_TRT ? launch_fused2_t<double, COLL_TRT>(s, a, macros, st)
+                                        : launch_fused2_t<double, COLL_MRT>(s, a, macros, st);
+    } else {
+        e = s->cfg.collision == LBM_SRT ? launch_fused2_t<float, COLL_SRT>(s, a, macros, st)
+          : s->cfg.collision == LBM_TRT ? launch_fused2_t<float, COLL_TRT>(s, a, macros, st)
+                                        : launch_fused2_t<float, COLL_MRT>(s, a, macros, st);
+    }
+    if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("fused two-step launch: ") + cudaGetErrorString(e));
+    s->launches++;
+    s->cur ^= 1; s->side ^= 1; s->steps += 2;
+    return LBM_OK;
+}
+
 // Launch one pass over a row region. rows: begin, count, stride.
 static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin, int row_count, int row_stride,
                        bool gather, bool macros, int mode, cudaStream_t st) {
@@ -978,7 +1153,7 @@ int lbm_destroy(lbm_handle_t s) {
     cudaFree(s->pi_eq); cudaFree(s->rho_prev);
     cudaFree(s->active); cudaFree(s->usum);
     cudaFree(s->staging); cudaFree(s->scratch);
-    for (int i = 0; i < 2; ++i) if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
+    for (int i = 0; i < 4; ++i) if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
     if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
     delete s;
     return LBM_OK;
@@ -1017,6 +1192,8 @@ int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
     if (const char* ev = getenv("LBM_B200_VEC_F32")) s->vec_f32 = (atoi(ev) == 2 || atoi(ev) == 4) ? atoi(ev) : 1;
     if (const char* ev = getenv("LBM_B200_GRAPH")) s->use_graph = atoi(ev) != 0;
     if (const char* ev = getenv("LBM_B200_PDL")) s->use_pdl = atoi(ev) != 0;
+    if (const char* ev = getenv("LBM_B200_FUSED2")) s->use_fused2 = atoi(ev) != 0;
+    if (const char* ev = getenv("LBM_B200_FUSED2_TILE")) s->fused2_tile = atoi(ev);
     if (const char* ev = getenv("LBM_B200_TMA_VARIANT")) s->tma_variant = atoi(ev) % LBM_TMA_VARIANTS;
     if (const char* ev = getenv("LBM_B200_TMA_CTAS")) s->tma_ctas_per_sm = atoi(ev) > 0 ? atoi(ev) : 1;
 #define CKD(call)                                                                       \
@@ -1045,10 +1222,10 @@ int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
     CKD(cudaMalloc(&s->ux, mbytes));
     CKD(cudaMalloc(&s->uy, mbytes));
     CKD(cudaMemset(s->rho, 0, mbytes)); CKD(cudaMemset(s->ux, 0, mbytes)); CKD(cudaMemset(s->uy, 0, mbytes));
-    CKD(cudaMalloc(&s->rho_lid, (size_t)cfg->batch * s->pitch * s->esz));
-    CKD(cudaMemset(s->rho_lid, 0, (size_t)cfg->batch * s->pitch * s->esz));
-    CKD(cudaMalloc(&s->carry, (size_t)cfg->batch * 4 * s->esz));
-    CKD(cudaMemset(s->carry, 0, (size_t)cfg->batch * 4 * s->esz));
+    CKD(cudaMalloc(&s->rho_lid, 2 * (size_t)cfg->batch * s->pitch * s->esz));      // two halves (see `side`)
+    CKD(cudaMemset(s->rho_lid, 0, 2 * (size_t)cfg->batch * s->pitch * s->esz));
+    CKD(cudaMalloc(&s->carry, 2 * (size_t)cfg->batch * 4 * s->esz));
+    CKD(cudaMemset(s->carry, 0, 2 * (size_t)cfg->batch * 4 * s->esz));
     CKD(cudaMalloc(&s->cav, sizeof(CavityParams) * cfg->batch));
     if (cfg->turb) {
         CKD(cudaMalloc(&s->pi_eq, mbytes));
@@ -1111,6 +1288,7 @@ int lbm_init_equilibrium(lbm_handle_t s) {
     if (rc) return rc;
     rc = sync_params(s, 0);
     if (rc) return rc;
+    s->side = 0;
     StepArgs a = make_args(s, nullptr, s->f[0]);
     dim3 grid((s->cfg.nx + 255) / 256, 1, s->cfg.batch);
     for (int off = 0; off < s->nyl; off += 65535) {
@@ -1187,6 +1365,7 @@ int lbm_upload_f(lbm_handle_t s, const void* f, int on_device, void* stream) {
     rc = move_planes(s, const_cast<void*>(f), fcav, on_device != 0, true, s->cfg.batch, 9, s->f[0], s->plane, s->cavity,
                      s->pitch, st);
     if (rc) return rc;
+    s->side = 0;
     StepArgs a = make_args(s, s->f[0], nullptr);
     if (s->esz == 8) lbm_seed_carry<double><<<s->cfg.batch, 4, 0, st>>>(a);
     else lbm_seed_carry<float><<<s->cfg.batch, 4, 0, st>>>(a);
@@ -1282,22 +1461,39 @@ int lbm_buffer_ptr(lbm_handle_t s, int which, void** ptr) {
 #define LBM_GRAPH_STEPS 32
 #define LBM_GRAPH_MAX_NODES (1 << 22)   // only launch-latency-bound sizes take the graph path
 
-static int build_graph(lbm_solver* s, int parity) {
+// Below this many nodes the 64x8 / 32x16 tiles no longer fill the 148 SMs several times over and the one-step kernel
+// (one wave of dependent L2 loads) is as fast or faster: 384^2 3.6 vs 3.9 us/step, 640^2 equal, 1024^2 46 -> 64 GLUPS.
+#define LBM_FUSED2_MIN_NODES 600000
+
+static bool fused2_usable(const lbm_solver* s) {
+    return s->use_fused2 && (long long)s->cfg.nx * s->cfg.ny * s->cfg.batch >= LBM_FUSED2_MIN_NODES && s->nyl == s->cfg.ny && !s->cfg.turb && s->engine == LBM_ENGINE_LDG && !s->active &&
+           s->cfg.semantics == LBM_SEMANTICS_C;
+}
+
+// Capture LBM_GRAPH_STEPS steady steps (fused two-step launches when usable) starting from the current (cur, side);
+// an even number of launches of either kind returns to the same (cur, side), so the graph is re-launchable as is.
+static int build_graph(lbm_solver* s, int key) {
     if (!s->capture_stream) CK(cudaStreamCreateWithFlags(&s->capture_stream, cudaStreamNonBlocking));
     cudaGraph_t g = nullptr;
     CK(cudaStreamBeginCapture(s->capture_stream, cudaStreamCaptureModeThreadLocal));
     int rc = LBM_OK;
-    int cur = parity;
-    const int64_t launches0 = s->launches;
-    for (int i = 0; i < LBM_GRAPH_STEPS && rc == LBM_OK; ++i) {
-        rc = launch_pass(s, s->f[cur], s->f[cur ^ 1], 0, s->nyl, 1, true, false, MODE_STEP, s->capture_stream);
-        cur ^= 1;
+    const int cur0 = s->cur, side0 = s->side;
+    const int64_t launches0 = s->launches, steps0 = s->steps;
+    const bool fused = fused2_usable(s);
+    for (int i = 0; i < LBM_GRAPH_STEPS && rc == LBM_OK; i += fused ? 2 : 1) {
+        if (fused) {
+            rc = launch_fused2(s, false, s->capture_stream);
+        } else {
+            rc = launch_pass(s, s->f[s->cur], s->f[s->cur ^ 1], 0, s->nyl, 1, true, false, MODE_STEP, s->capture_stream);
+            s->cur ^= 1;
+        }
     }
-    s->launches = launches0;            // counted when the graph is launched, not when it is captured
+    // counted when the graph is launched, not when it is captured
+    s->cur = cur0; s->side = side0; s->launches = launches0; s->steps = steps0;
     cudaError_t e = cudaStreamEndCapture(s->capture_stream, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&s->graph[parity], g, 0);
+    e = cudaGraphInstantiate(&s->graph[key], g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
     return LBM_OK;
@@ -1308,32 +1504,40 @@ int lbm_step(lbm_handle_t s, int nsteps, int write_macros, void* stream) {
     if (nsteps < 0) return fail(LBM_EINVAL, "nsteps < 0");
     if (s->nyl != s->cfg.ny && nsteps > 1)
         return fail(LBM_ESTATE, "a y-strip handle needs a halo exchange between steps: use lbm_step_region/lbm_swap");
+    if (nsteps == 0) return LBM_OK;
+    int rc = set_device(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = sync_params(s, st);
+    if (rc) return rc;
     if (s->cfg.semantics == LBM_SEMANTICS_A) {
-        int rc = set_device(s);
-        if (rc) return rc;
-        rc = sync_params(s, (cudaStream_t)stream);
-        if (rc) return rc;
-        for (int i = 0; i < nsteps; ++i) { rc = step_A(s, (cudaStream_t)stream); if (rc) return rc; }
+        for (int i = 0; i < nsteps; ++i) { rc = step_A(s, st); if (rc) return rc; }
         return LBM_OK;
     }
     int left = nsteps;
     const bool small = (long long)s->cfg.nx * s->nyl * s->cfg.batch <= LBM_GRAPH_MAX_NODES;
     while (left > 0) {
-        const bool last = (left == 1);
-        // steady state (post-collision buffer, no macro output) in blocks of LBM_GRAPH_STEPS: one graph launch
-        if (s->use_graph && small && !s->pre && left > LBM_GRAPH_STEPS) {
-            int rc = set_device(s);
-            if (rc) return rc;
-            rc = sync_params(s, (cudaStream_t)stream);
-            if (rc) return rc;
-            if (!s->graph[s->cur]) { rc = build_graph(s, s->cur); if (rc) return rc; }
-            CK(cudaGraphLaunch(s->graph[s->cur], (cudaStream_t)stream));
-            s->launches += LBM_GRAPH_STEPS;
-            s->steps += LBM_GRAPH_STEPS;
-            left -= LBM_GRAPH_STEPS;
-            continue;
+        if (!s->pre) {
+            // steady state in blocks of LBM_GRAPH_STEPS: one graph launch (launch-latency-bound sizes only)
+            if (s->use_graph && small && left > LBM_GRAPH_STEPS) {
+                const int key = s->cur * 2 + s->side;
+                const bool fused = fused2_usable(s);
+                if (!s->graph[key]) { rc = build_graph(s, key); if (rc) return rc; }
+                CK(cudaGraphLaunch(s->graph[key], st));
+                s->launches += fused ? LBM_GRAPH_STEPS / 2 : LBM_GRAPH_STEPS;
+                s->steps += LBM_GRAPH_STEPS;
+                left -= LBM_GRAPH_STEPS;
+                continue;
+            }
+            // temporal blocking: two steps per launch
+            if (left >= 2 && fused2_usable(s)) {
+                rc = launch_fused2(s, write_macros && left == 2, st);
+                if (rc) return rc;
+                left -= 2;
+                continue;
+            }
         }
-        int rc = lbm_step_region(s, LBM_REGION_ALL, (write_macros && last) ? 1 : 0, stream);
+        rc = lbm_step_region(s, LBM_REGION_ALL, (write_macros && left == 1) ? 1 : 0, stream);
         if (rc) return rc;
         lbm_swap(s);
         --left;
@@ -1506,7 +1710,7 @@ int lbm_set_active(lbm_handle_t s, const int32_t* active, void* stream) {
     if (!s->active) {
         CK(cudaMalloc(&s->active, sizeof(int) * nb));
         s->active_host.assign(nb, 1);
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 4; ++i)
             if (s->graph[i]) { cudaGraphExecDestroy(s->graph[i]); s->graph[i] = nullptr; }   // kernel args change
     }
     const size_t cav_bytes = (size_t)s->cavity * s->esz;

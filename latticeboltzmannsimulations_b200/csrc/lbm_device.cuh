@@ -35,6 +35,8 @@ struct StepArgs {
     void* uy;
     void* rho_lid;             // [batch][pitch]
     void* carry;               // [batch][4]
+    void* rho_lid_out;         // fused two-step kernel: side buffers written for the state two steps ahead (the other
+    void* carry_out;           //   half of the double-buffered allocation); single-step kernels update in place
     void* pi_eq;               // [batch][nyl][pitch]  sum_k cx cy feq_k of the previous step (Smagorinsky only)
     void* rho_prev;            // [batch][nyl][pitch]  rho of the previous step            (Smagorinsky only)
     const CavityParams* cav;   // [batch]

@@ -408,7 +408,8 @@ def test_tma_engine_parity(dtype):
 
 
 @pytest.mark.parametrize("env", [{"LBM_B200_VEC_F64": "2", "LBM_B200_VEC_F32": "2"}, {"LBM_B200_VEC_F32": "1"},
-                                 {"LBM_B200_GRAPH": "0", "LBM_B200_PDL": "0"}])
+                                 {"LBM_B200_GRAPH": "0", "LBM_B200_PDL": "0"}, {"LBM_B200_FUSED2": "0"},
+                                 {"LBM_B200_FUSED2_TILE": "0"}])
 def test_kernel_variants_are_bit_identical(env, monkeypatch):
     """Every compiled data-movement variant (scalar / 2 / 4 nodes per thread, with and without graphs and programmatic
     dependent launch) produces the same bits as the default configuration."""
