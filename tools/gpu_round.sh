@@ -13,11 +13,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "ncu launches rc=$?"
 # full capture of the dominant kernel (fp64 MRT then fp32 MRT), 2 launches each
 python tools/quick_perf.py 4096 4096 float64 > gpurun_out/${TAG}_plain64.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:lbm_step -s 25 -c 2 -o gpurun_out/${TAG}_f64 -f \
+ncu --set full --clock-control none --import-source on -k regex:lbm_step -s 14 -c 2 -o gpurun_out/${TAG}_f64 -f \
     python tools/quick_perf.py 4096 4096 float64 > gpurun_out/${TAG}_ncu64.log 2>&1
 echo "ncu f64 rc=$?"
 python tools/quick_perf.py 4096 4096 float32 > gpurun_out/${TAG}_plain32.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:lbm_step -s 25 -c 2 -o gpurun_out/${TAG}_f32 -f \
+ncu --set full --clock-control none --import-source on -k regex:lbm_step -s 14 -c 2 -o gpurun_out/${TAG}_f32 -f \
     python tools/quick_perf.py 4096 4096 float32 > gpurun_out/${TAG}_ncu32.log 2>&1
 echo "ncu f32 rc=$?"
 cat gpurun_out/${TAG}_plain64.log gpurun_out/${TAG}_plain32.log
