@@ -70,7 +70,10 @@ typedef struct lbm_layout {
     int64_t rows;           /* stored rows per population plane = ny_local + 2 (ghost row first and last) */
     int64_t plane;          /* elements per population plane = rows * pitch */
     int64_t cavity;         /* elements per cavity = 9 * plane */
-    int64_t state_bytes;    /* bytes of one A/B buffer = batch * cavity * elem_size */
+    int64_t state_bytes;    /* bytes of one A/B buffer = (batch * cavity + batch * 6 * pitch) * elem_size */
+    int64_t ghost2_offset;  /* elements from the buffer start to the tail [batch][top|bottom][3][pitch]: the SECOND
+                               ghost rows used by the two-step kernel on a y-strip -- top: populations 4,7,8 of global
+                               row y0-2, bottom: populations 2,5,6 of global row y0+ny_local+1 */
 } lbm_layout_t;
 
 const char* lbm_last_error(void);
@@ -112,6 +115,15 @@ int lbm_step(lbm_handle_t h, int nsteps, int write_macros, void* stream);
  * Used by the y-strip driver: EDGE rows first, halo rows exchanged while INTERIOR runs. */
 int lbm_step_region(lbm_handle_t h, int region, int write_macros, void* stream);
 int lbm_swap(lbm_handle_t h);
+/* Same for the temporal-blocking kernel: TWO steps of a row region in one launch (the state must be post-collision,
+ * i.e. at least one ordinary step taken since the last upload, and ny_local >= 2); lbm_swap2() completes the double
+ * step.  Before the next (double) step the ghost rows of the written buffer must hold, from the strip above, all of
+ * populations {0,1,3,4,7,8} of its last row and {4,7,8} of the row before it (-> ghost2 top), and from the strip
+ * below {0,1,3,2,5,6} of its first row and {2,5,6} of its second row (-> ghost2 bottom). */
+int lbm_step2_region(lbm_handle_t h, int region, int write_macros, void* stream);
+int lbm_swap2(lbm_handle_t h);
+/* 1 if lbm_step2_region can be used right now (temporal blocking enabled, post-collision state, ny_local >= 2, ...). */
+int lbm_step2_available(lbm_handle_t h);
 /* Device pointers of the buffer being read (which = 0) / written (which = 1) by the next lbm_step_region. */
 int lbm_buffer_ptr(lbm_handle_t h, int which, void** ptr);
 

@@ -25,7 +25,7 @@ SEMANTICS = {"C": 0, "A": 1}
 SYMBOLS = [
     "lbm_last_error", "lbm_abi_version", "lbm_device_count", "lbm_state_bytes", "lbm_create", "lbm_destroy",
     "lbm_get_layout", "lbm_set_reynolds", "lbm_set_rates", "lbm_init_equilibrium", "lbm_upload_f",
-    "lbm_download_f", "lbm_step", "lbm_step_region", "lbm_swap", "lbm_buffer_ptr", "lbm_get_macros",
+    "lbm_download_f", "lbm_step", "lbm_step_region", "lbm_swap", "lbm_step2_region", "lbm_swap2", "lbm_step2_available", "lbm_buffer_ptr", "lbm_get_macros",
     "lbm_get_macros_current", "lbm_equilibrium", "lbm_mean_u", "lbm_set_active", "lbm_diagnostics", "lbm_sync", "lbm_get_counters", "lbm_engine_name",
 ]
 
@@ -45,7 +45,7 @@ class Config(C.Structure):
 
 class Layout(C.Structure):
     _fields_ = [("elem_size", C.c_int64), ("pitch", C.c_int64), ("rows", C.c_int64), ("plane", C.c_int64),
-                ("cavity", C.c_int64), ("state_bytes", C.c_int64)]
+                ("cavity", C.c_int64), ("state_bytes", C.c_int64), ("ghost2_offset", C.c_int64)]
 
 
 _lib = None
@@ -86,6 +86,9 @@ def load():
     lib.lbm_step.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
     lib.lbm_step_region.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
     lib.lbm_swap.argtypes = [H]
+    lib.lbm_step2_region.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
+    lib.lbm_swap2.argtypes = [H]
+    lib.lbm_step2_available.argtypes = [H]
     lib.lbm_buffer_ptr.argtypes = [H, C.c_int, C.POINTER(C.c_void_p)]
     lib.lbm_get_macros.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.lbm_get_macros_current.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]

@@ -332,7 +332,8 @@ __global__ void __launch_bounds__(256) lbm_step_vec(const StepArgs a) {
 // The per-node arithmetic is the shared node_update()/wall_rule(), so results are bit-identical to two one-step
 // launches.  The lid density and corner carries of the intermediate state live in shared memory; those of the
 // final state go to the other half of the double-buffered side arrays (a neighbouring CTA may still need the old
-// ones for its halo ring).  Whole cavities only (a y-strip would need a two-row halo exchange).
+// ones for its halo ring).  On a y-strip the ring of the first / last tile row lies in the ghost row, whose own
+// sub-step 1 needs one more row from the neighbour: the second ghost rows (`ghost2`, three populations each).
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, int TX_, int TY_> struct Fused2Cfg {
     static constexpr int TX = TX_, TY = TY_;
@@ -351,31 +352,37 @@ __global__ void __launch_bounds__(256, MINB) lbm_step_fused2(const StepArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int b = blockIdx.z;
-    const int x0 = blockIdx.x * Cfg::TX, y0 = blockIdx.y * Cfg::TY;   // tile origin (whole cavity: local row == y)
+    const int x0 = blockIdx.x * Cfg::TX;
+    const int yl0 = (a.row_begin + blockIdx.y) * Cfg::TY;          // first LOCAL row of the tile (row_begin in tile rows)
     const T* __restrict__ src = static_cast<const T*>(a.src) + (long long)b * a.cavity;
     T* __restrict__ dst = static_cast<T*>(a.dst) + (long long)b * a.cavity;
     const long long P = a.plane;
     const Rates<T> r(a.cav[b]);
     const T* carry_in = static_cast<const T*>(a.carry) + b * 4;
     const T* rl_in = static_cast<const T*>(a.rho_lid) + (long long)b * a.pitch;
+    // second ghost rows of a y-strip (neighbour's rows y0-2: populations 4,7,8 and y0+nyl+1: populations 2,5,6)
+    const T* g2top = static_cast<const T*>(a.ghost2) + (long long)b * 6 * a.pitch;
+    const T* g2bot = g2top + 3 * a.pitch;
 
     // ---- sub-step 1 on the grown tile: global (state t) -> shared (state t+1) ----
     for (int i = threadIdx.x; i < Cfg::PLANE; i += blockDim.x) {
         const int ly = i / Cfg::RX, lx = i - ly * Cfg::RX;
-        const int x = x0 - 1 + lx, y = y0 - 1 + ly;
-        if (x < 0 || x >= a.nx || y < 0 || y >= a.ny) continue;
+        const int x = x0 - 1 + lx, yl = yl0 - 1 + ly;               // yl in [-1, nyl]: the ring may sit in a ghost row
+        const int y = a.y0 + yl;
+        if (x < 0 || x >= a.nx || y < 0 || y >= a.ny || yl > a.nyl) continue;
         const bool left = (x == 0), right = (x == a.nx - 1), lid = (y == 0), bot = (y == a.ny - 1);
-        const long long rc = (long long)(y + 1) * a.pitch + x, ru = rc - a.pitch, rd = rc + a.pitch;
+        const long long rc = (long long)(yl + 1) * a.pitch + x, ru = rc - a.pitch, rd = rc + a.pitch;
+        const bool up2 = (yl == -1), dn2 = (yl == a.nyl);            // row above / below comes from the second ghost row
         T f[9];
         f[0] = src[rc];
         f[1] = left ? (T)0 : src[1 * P + rc - 1];
-        f[2] = bot ? (T)0 : src[2 * P + rd];
         f[3] = right ? (T)0 : src[3 * P + rc + 1];
-        f[4] = lid ? (T)0 : src[4 * P + ru];
-        f[5] = (left || bot) ? (T)0 : src[5 * P + rd - 1];
-        f[6] = (right || bot) ? (T)0 : src[6 * P + rd + 1];
-        f[7] = (right || lid) ? (T)0 : src[7 * P + ru + 1];
-        f[8] = (left || lid) ? (T)0 : src[8 * P + ru - 1];
+        f[2] = bot ? (T)0 : (dn2 ? g2bot[x] : src[2 * P + rd]);
+        f[5] = (left || bot) ? (T)0 : (dn2 ? g2bot[a.pitch + x - 1] : src[5 * P + rd - 1]);
+        f[6] = (right || bot) ? (T)0 : (dn2 ? g2bot[2 * a.pitch + x + 1] : src[6 * P + rd + 1]);
+        f[4] = lid ? (T)0 : (up2 ? g2top[x] : src[4 * P + ru]);
+        f[7] = (right || lid) ? (T)0 : (up2 ? g2top[a.pitch + x + 1] : src[7 * P + ru + 1]);
+        f[8] = (left || lid) ? (T)0 : (up2 ? g2top[2 * a.pitch + x - 1] : src[8 * P + ru - 1]);
         if (left || right || lid || bot) {
             const int slot = corner_slot(left, right, lid, bot);
             const T stale = slot >= 0 ? carry_in[slot] : (T)0;
@@ -394,8 +401,9 @@ __global__ void __launch_bounds__(256, MINB) lbm_step_fused2(const StepArgs a) {
     // ---- sub-step 2 on the tile: shared (state t+1) -> global (state t+2) ----
     for (int i = threadIdx.x; i < Cfg::TX * Cfg::TY; i += blockDim.x) {
         const int ty = i / Cfg::TX, tx = i - ty * Cfg::TX;
-        const int x = x0 + tx, y = y0 + ty;
-        if (x >= a.nx || y >= a.ny) continue;
+        const int x = x0 + tx, yl = yl0 + ty;
+        const int y = a.y0 + yl;
+        if (x >= a.nx || yl >= a.nyl) continue;
         const bool left = (x == 0), right = (x == a.nx - 1), lid = (y == 0), bot = (y == a.ny - 1);
         const int c = (ty + 1) * Cfg::RX + (tx + 1);               // this node inside the grown tile
         const int u = c - Cfg::RX, d = c + Cfg::RX;                // row y-1 / y+1
@@ -419,11 +427,11 @@ __global__ void __launch_bounds__(256, MINB) lbm_step_fused2(const StepArgs a) {
         T rho, ux, uy;
         node_update<T, COLL, MACROS>(f, r, left, right, lid, bot, rho, ux, uy);
         if (lid) static_cast<T*>(a.rho_lid_out)[(long long)b * a.pitch + x] = rho;
-        const long long rc = (long long)(y + 1) * a.pitch + x;
+        const long long rc = (long long)(yl + 1) * a.pitch + x;
 #pragma unroll
         for (int k = 0; k < 9; ++k) dst[k * P + rc] = f[k];
         if (MACROS) {
-            const long long m = (long long)b * a.mplane + (long long)y * a.pitch + x;
+            const long long m = (long long)b * a.mplane + (long long)yl * a.pitch + x;
             static_cast<T*>(a.rho)[m] = rho;
             static_cast<T*>(a.ux)[m] = ux;
             static_cast<T*>(a.uy)[m] = uy;
@@ -967,6 +975,18 @@ static void launch_vec_coll(int coll, const StepArgs& a, const Launch& L, bool m
     }
 }
 
+// Below this many nodes the 64x8 / 32x16 tiles no longer fill the 148 SMs several times over and the one-step kernel
+// (one wave of dependent L2 loads) is as fast or faster: 384^2 3.6 vs 3.9 us/step, 640^2 equal, 1024^2 46 -> 64 GLUPS.
+#define LBM_FUSED2_MIN_NODES 600000
+
+// Temporal blocking applies to this handle at all (whole cavity or y-strip of at least two rows)?
+static bool fused2_capable(const lbm_solver* s) {
+    return s->use_fused2 && (long long)s->cfg.nx * s->cfg.ny * s->cfg.batch >= LBM_FUSED2_MIN_NODES && s->nyl >= 2 &&
+           !s->cfg.turb && s->engine == LBM_ENGINE_LDG && !s->active && s->cfg.semantics == LBM_SEMANTICS_C;
+}
+// ... and to lbm_step, which owns whole cavities only
+static bool fused2_usable(const lbm_solver* s) { return fused2_capable(s) && s->nyl == s->cfg.ny; }
+
 // ---- fused two-step launch ------------------------------------------------------------------------------------
 template <typename T, int COLL, int TX, int TY, int MINB>
 static cudaError_t launch_fused2_tile(lbm_solver* s, const StepArgs& a, bool macros, cudaStream_t st) {
@@ -978,15 +998,19 @@ static cudaError_t launch_fused2_tile(lbm_solver* s, const StepArgs& a, bool mac
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    dim3 grid((s->cfg.nx + Cfg::TX - 1) / Cfg::TX, (s->cfg.ny + Cfg::TY - 1) / Cfg::TY, s->cfg.batch);
+    // a.row_begin / a.row_count arrive in LOCAL ROWS (multiples of the tile height, see fused2_bands): convert
+    StepArgs t = a;
+    t.row_begin = a.row_begin / Cfg::TY;
+    const int tile_rows = (a.row_count + Cfg::TY - 1) / Cfg::TY;
+    dim3 grid((s->cfg.nx + Cfg::TX - 1) / Cfg::TX, tile_rows, s->cfg.batch);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(256, 1, 1); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = s->use_pdl ? 1 : 0;
-    if (macros) return cudaLaunchKernelEx(&cfg, lbm_step_fused2<T, COLL, true, TX, TY, MINB>, a);
-    return cudaLaunchKernelEx(&cfg, lbm_step_fused2<T, COLL, false, TX, TY, MINB>, a);
+    if (macros) return cudaLaunchKernelEx(&cfg, lbm_step_fused2<T, COLL, true, TX, TY, MINB>, t);
+    return cudaLaunchKernelEx(&cfg, lbm_step_fused2<T, COLL, false, TX, TY, MINB>, t);
 }
 
 template <typename T, int COLL>
@@ -1005,9 +1029,23 @@ static cudaError_t launch_fused2_t(lbm_solver* s, const StepArgs& a, bool macros
     }
 }
 
-// Two steps in one launch: cur -> cur^1, side -> side^1.
-static int launch_fused2(lbm_solver* s, bool macros, cudaStream_t st) {
+// Tile height of the fused kernel in use (needed to cut a strip into edge / interior bands of whole tile rows).
+static int fused2_tile_height(const lbm_solver* s) {
+    const int variant = s->fused2_tile >= 0 ? s->fused2_tile : (s->esz == 8 ? 3 : 4);
+    switch (variant) {
+        case 1: case 3: case 7: return 8;
+        case 5: return 12;
+        default: return 16;
+    }
+}
+
+// Fused launch over local rows [row_begin, row_begin + row_count) (row_begin a multiple of the tile height); no
+// state change -- the caller flips cur / side once every band of the double step has been launched.
+static int launch_fused2_rows(lbm_solver* s, int row_begin, int row_count, bool macros, cudaStream_t st) {
+    if (row_count <= 0) return LBM_OK;
     StepArgs a = make_args(s, s->f[s->cur], s->f[s->cur ^ 1]);
+    a.row_begin = row_begin; a.row_count = row_count;
+    a.ghost2 = (char*)s->f[s->cur] + (size_t)s->cfg.batch * s->cavity * s->esz;
     cudaError_t e;
     if (s->cfg.dtype == LBM_F64) {
         e = s->cfg.collision == LBM_SRT ? launch_fused2_t<double, COLL_SRT>(s, a, macros, st)
@@ -1020,6 +1058,13 @@ static int launch_fused2(lbm_solver* s, bool macros, cudaStream_t st) {
     }
     if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("fused two-step launch: ") + cudaGetErrorString(e));
     s->launches++;
+    return LBM_OK;
+}
+
+// Two steps in one launch over the whole strip: cur -> cur^1, side -> side^1.
+static int launch_fused2(lbm_solver* s, bool macros, cudaStream_t st) {
+    int rc = launch_fused2_rows(s, 0, s->nyl, macros, st);
+    if (rc) return rc;
     s->cur ^= 1; s->side ^= 1; s->steps += 2;
     return LBM_OK;
 }
@@ -1129,7 +1174,8 @@ static void layout_of(const lbm_config_t* c, int nyl, lbm_layout_t* L) {
     L->rows = nyl + 2;
     L->plane = L->rows * L->pitch;
     L->cavity = 9 * L->plane;
-    L->state_bytes = (int64_t)c->batch * L->cavity * L->elem_size;
+    L->ghost2_offset = (int64_t)c->batch * L->cavity;            // tail: [batch][top|bottom][3][pitch]
+    L->state_bytes = ((int64_t)c->batch * L->cavity + (int64_t)c->batch * 6 * L->pitch) * L->elem_size;
 }
 
 int lbm_state_bytes(const lbm_config_t* cfg, size_t* bytes) {
@@ -1450,6 +1496,40 @@ int lbm_swap(lbm_handle_t s) {
     return LBM_OK;
 }
 
+int lbm_step2_available(lbm_handle_t s) { return s && fused2_capable(s) && !s->pre ? 1 : 0; }
+
+int lbm_step2_region(lbm_handle_t s, int region, int write_macros, void* stream) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    if (!fused2_capable(s) || s->pre)
+        return fail(LBM_ESTATE, "two-step kernel not available for this handle/state (see lbm_step2_available)");
+    int rc = set_device(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = sync_params(s, st);
+    if (rc) return rc;
+    const int ty = fused2_tile_height(s), nyl = s->nyl;
+    const int ntr = (nyl + ty - 1) / ty;                              // tile rows of the strip
+    const int nb = (nyl % ty == 1 && ntr > 1) ? 2 : 1;                // bottom band must contain rows nyl-2 and nyl-1
+    const bool split = ntr > 1 + nb;                                  // otherwise the edge bands are the whole strip
+    const int bot0 = (ntr - nb) * ty;                                 // first row of the bottom band
+    const bool wm = write_macros != 0;
+    if (region == LBM_REGION_ALL || (region == LBM_REGION_EDGE && !split)) return launch_fused2_rows(s, 0, nyl, wm, st);
+    if (region == LBM_REGION_EDGE) {
+        rc = launch_fused2_rows(s, 0, ty, wm, st);
+        if (rc) return rc;
+        return launch_fused2_rows(s, bot0, nyl - bot0, wm, st);
+    }
+    if (region == LBM_REGION_INTERIOR) return split ? launch_fused2_rows(s, ty, bot0 - ty, wm, st) : LBM_OK;
+    return fail(LBM_EINVAL, "bad region");
+}
+
+int lbm_swap2(lbm_handle_t s) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    if (s->cfg.semantics == LBM_SEMANTICS_A) return fail(LBM_ESTATE, "semantics A has no region stepping: use lbm_step");
+    s->cur ^= 1; s->side ^= 1; s->steps += 2;
+    return LBM_OK;
+}
+
 int lbm_buffer_ptr(lbm_handle_t s, int which, void** ptr) {
     if (!s || !ptr) return fail(LBM_EINVAL, "NULL argument");
     *ptr = s->f[which ? (s->cur ^ 1) : s->cur];
@@ -1461,14 +1541,7 @@ int lbm_buffer_ptr(lbm_handle_t s, int which, void** ptr) {
 #define LBM_GRAPH_STEPS 32
 #define LBM_GRAPH_MAX_NODES (1 << 22)   // only launch-latency-bound sizes take the graph path
 
-// Below this many nodes the 64x8 / 32x16 tiles no longer fill the 148 SMs several times over and the one-step kernel
-// (one wave of dependent L2 loads) is as fast or faster: 384^2 3.6 vs 3.9 us/step, 640^2 equal, 1024^2 46 -> 64 GLUPS.
-#define LBM_FUSED2_MIN_NODES 600000
 
-static bool fused2_usable(const lbm_solver* s) {
-    return s->use_fused2 && (long long)s->cfg.nx * s->cfg.ny * s->cfg.batch >= LBM_FUSED2_MIN_NODES && s->nyl == s->cfg.ny && !s->cfg.turb && s->engine == LBM_ENGINE_LDG && !s->active &&
-           s->cfg.semantics == LBM_SEMANTICS_C;
-}
 
 // Capture LBM_GRAPH_STEPS steady steps (fused two-step launches when usable) starting from the current (cur, side);
 // an even number of launches of either kind returns to the same (cur, side), so the graph is re-launchable as is.

@@ -37,6 +37,7 @@ struct StepArgs {
     void* carry;               // [batch][4]
     void* rho_lid_out;         // fused two-step kernel: side buffers written for the state two steps ahead (the other
     void* carry_out;           //   half of the double-buffered allocation); single-step kernels update in place
+    const void* ghost2;        // fused kernel on a y-strip: [batch][top|bottom][3][pitch] second ghost rows of `src`
     void* pi_eq;               // [batch][nyl][pitch]  sum_k cx cy feq_k of the previous step (Smagorinsky only)
     void* rho_prev;            // [batch][nyl][pitch]  rho of the previous step            (Smagorinsky only)
     const CavityParams* cav;   // [batch]

@@ -3,7 +3,8 @@
 * ``StripCavity`` -- ONE large cavity cut into contiguous y-strips (rows are x-contiguous in the device layout, so a
   strip boundary is a whole row).  The update of a row reads only rows y-1, y, y+1, hence exactly one
   nearest-neighbour exchange per step: across each interface the three populations that cross it
-  (towards larger y: k in {4,7,8}; towards smaller y: k in {2,5,6}), ``3 * nx`` values per direction.  Per step
+  (towards larger y: k in {4,7,8}; towards smaller y: k in {2,5,6}), ``3 * nx`` values per direction -- nine rows
+  per direction when the two-step (temporal blocking) kernel is used, which recomputes the ghost row.  Per step
   the two edge rows of the strip are updated first on a halo stream, their crossing populations are sent straight
   from / received straight into the population buffers (row views, no pack kernels) with grouped NCCL send/recv,
   and the interior rows are updated concurrently on the main stream.  The reference has no multi-GPU path at all
@@ -39,42 +40,94 @@ def partition_rows(ny: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
-def halo_plan(rank: int, world: int, nyl: int):
-    """P2P plan of one step for ``rank``: list of (kind, peer, population, stored_row).
+AXIS_POPS = (0, 1, 3)     # c_y = 0: stay in their row
 
-    Stored row r holds local row r-1; stored rows 0 and nyl+1 are the ghost rows.  Sends read the freshly written
-    edge rows, receives land in the ghost rows of the same (destination) buffer.
+
+def halo_plan(rank: int, world: int, nyl: int, deep: bool = False):
+    """P2P plan of one (double) step for ``rank``: list of ``(kind, peer, spec)``.
+
+    ``spec`` is ``("row", k, stored_row)`` for a row of population k in the main buffer (stored row r holds local
+    row r-1; stored rows 0 and nyl+1 are the ghost rows) or ``("g2", which, j)`` for the j-th row of the second
+    ghost rows (which = 0: above the strip, populations 4,7,8; 1: below, populations 2,5,6).  Sends read the freshly
+    written edge rows, receives land in the ghost rows of the same (destination) buffer.  Matching sends and
+    receives are listed in the same order on both sides.
+
+    ``deep=False``: what one-step kernels need -- the three crossing populations of the adjacent row.
+    ``deep=True``: what the two-step (temporal blocking) kernel needs -- it recomputes the ghost row's own first
+    sub-step, so it also wants the ghost row's in-row populations and the crossing populations of the row beyond it:
+    nine rows per direction and interface.  A superset of the shallow plan, valid for one-step kernels too.
     """
     plan = []
-    if rank > 0:                       # interface with the strip above
-        for k in UP_POPS:
-            plan.append(("send", rank - 1, k, 1))
-        for k in DOWN_POPS:
-            plan.append(("recv", rank - 1, k, 0))
-    if rank < world - 1:               # interface with the strip below
-        for k in DOWN_POPS:
-            plan.append(("send", rank + 1, k, nyl))
-        for k in UP_POPS:
-            plan.append(("recv", rank + 1, k, nyl + 1))
+    if not deep:
+        if rank > 0:                       # interface with the strip above
+            plan += [("send", rank - 1, ("row", k, 1)) for k in UP_POPS]
+            plan += [("recv", rank - 1, ("row", k, 0)) for k in DOWN_POPS]
+        if rank < world - 1:               # interface with the strip below
+            plan += [("send", rank + 1, ("row", k, nyl)) for k in DOWN_POPS]
+            plan += [("recv", rank + 1, ("row", k, nyl + 1)) for k in UP_POPS]
+        return plan
+    if nyl < 2:
+        raise ValueError("the deep halo plan needs at least two rows per strip")
+    if rank > 0:
+        plan += [("send", rank - 1, ("row", k, 1)) for k in AXIS_POPS + UP_POPS]
+        plan += [("send", rank - 1, ("row", k, 2)) for k in UP_POPS]
+        plan += [("recv", rank - 1, ("row", k, 0)) for k in AXIS_POPS + DOWN_POPS]
+        plan += [("recv", rank - 1, ("g2", 0, j)) for j in range(3)]
+    if rank < world - 1:
+        plan += [("send", rank + 1, ("row", k, nyl)) for k in AXIS_POPS + DOWN_POPS]
+        plan += [("send", rank + 1, ("row", k, nyl - 1)) for k in DOWN_POPS]
+        plan += [("recv", rank + 1, ("row", k, nyl + 1)) for k in AXIS_POPS + UP_POPS]
+        plan += [("recv", rank + 1, ("g2", 1, j)) for j in range(3)]
     return plan
 
 
-class HaloExchanger:
-    """Executes ``halo_plan`` on a pair of A/B buffers given as tensors ``[9, nyl+2, pitch]`` (any device/backend)."""
+def strip_views(raw, layout, batch: int = 1):
+    """Views of one A/B allocation (a flat tensor of ``state_bytes``): main ``[9, rows, pitch]`` and second ghost
+    rows ``[2, 3, pitch]`` (``lbm_layout_t.ghost2_offset``).  Single-cavity strips only."""
+    if batch != 1:
+        raise ValueError("y-strips hold one cavity")
+    rows, pitch, off = int(layout.rows), int(layout.pitch), int(layout.ghost2_offset)
+    return raw[:off].view(9, rows, pitch), raw[off:off + 6 * pitch].view(2, 3, pitch)
 
-    def __init__(self, buffers, nx: int, rank: int, world: int, group=None):
+
+def plan_view(spec, main, g2, nx: int):
+    kind, a, b = spec
+    return main[a, b, :nx] if kind == "row" else g2[a, b, :nx]
+
+
+def exchange_local(plans, views, nx: int) -> None:
+    """Carry out the plans of all ranks inside one process (the single-GPU emulation used by the tests):
+    ``views[r] = (main, g2)`` of rank r's destination buffer."""
+    for r, plan in enumerate(plans):
+        sends = {}
+        for kind, peer, spec in plan:
+            if kind == "send":
+                sends.setdefault(peer, []).append(spec)
+        for peer, specs in sends.items():
+            recvs = [spec for kind, p2, spec in plans[peer] if kind == "recv" and p2 == r]
+            assert len(recvs) == len(specs)
+            for s_spec, r_spec in zip(specs, recvs):
+                plan_view(r_spec, *views[peer], nx).copy_(plan_view(s_spec, *views[r], nx))
+
+
+class HaloExchanger:
+    """Executes ``halo_plan`` on a pair of A/B buffers given as ``(main [9, nyl+2, pitch], g2 [2, 3, pitch])`` views
+    (any device/backend; ``g2`` may be None for the shallow plan)."""
+
+    def __init__(self, buffers, nx: int, rank: int, world: int, group=None, deep: bool = False):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.rank, self.world = rank, world
-        nyl = buffers[0].shape[1] - 2
-        self.plan = halo_plan(rank, world, nyl)
+        buffers = [b if isinstance(b, (tuple, list)) else (b, None) for b in buffers]
+        nyl = buffers[0][0].shape[1] - 2
+        self.plan = halo_plan(rank, world, nyl, deep)
         # ops are fixed per destination buffer: build them once (views of the persistent buffers)
         self._ops = []
-        for buf in buffers:
+        for main, g2 in buffers:
             ops = []
-            for kind, peer, k, row in self.plan:
-                view = buf[k, row, :nx]
+            for kind, peer, spec in self.plan:
+                view = plan_view(spec, main, g2, nx)
                 fn = dist.isend if kind == "send" else dist.irecv
                 ops.append(dist.P2POp(fn, view, peer, group=group))
             self._ops.append(ops)
@@ -110,11 +163,13 @@ class StripCavity:
         self.solver = CavitySolver(nx, ny, 1, dtype, collision, y0=self.y0, ny_local=self.nyl, device=self.device,
                                    engine=engine, ext_buffers=[t.data_ptr() for t in self._raw])
         lay = self.solver.layout
-        self.buffers = [t.view(9, int(lay.rows), int(lay.pitch)) for t in self._raw]
+        self.buffers = [strip_views(t, lay) for t in self._raw]
         self.solver.set_reynolds(Re, uLB)
         self.solver.init_equilibrium()
         self._ptr = {self._raw[0].data_ptr(): 0, self._raw[1].data_ptr(): 1}
-        self.halo = HaloExchanger(self.buffers, nx, self.rank, self.world, group)
+        # the deep plan (what the two-step kernel needs) whenever every strip has at least two rows
+        self.deep = all(n >= 2 for _, n in self.parts)
+        self.halo = HaloExchanger(self.buffers, nx, self.rank, self.world, group, deep=self.deep)
         self.overlap = overlap and self.nyl >= 3
         with torch.cuda.device(self.device):
             self.s_main = torch.cuda.Stream()
@@ -129,32 +184,42 @@ class StripCavity:
         return self._ptr[self.solver.buffer_ptr(1)]
 
     def step(self, nsteps: int = 1, write_macros: bool = False) -> None:
+        """Advance ``nsteps`` steps; two at a time with the temporal-blocking kernel when it is available (every
+        rank takes the same decision: it depends only on the global size and on the state being post-collision)."""
         torch = self.torch
         s = self.solver
-        for i in range(nsteps):
-            wm = write_macros and i == nsteps - 1
+        i = 0
+        while i < nsteps:
+            two = self.deep and (nsteps - i) >= 2 and s.step2_available()
+            n = 2 if two else 1
+            wm = write_macros and i + n == nsteps
+            region = s.step2_region if two else s.step_region
             dst = self._dst_index()
             if self.overlap:
                 with torch.cuda.stream(self.s_halo):
                     self.s_halo.wait_event(self.ev_main)              # interior of the previous step
-                    s.step_region(_capi.LBM_REGION_EDGE, wm, self.s_halo.cuda_stream)
+                    region(_capi.LBM_REGION_EDGE, wm, self.s_halo.cuda_stream)
                     for w in self.halo.exchange(dst):
                         w.wait()                                       # stream-side wait, the host runs ahead
                     new_halo = torch.cuda.Event()
                     new_halo.record(self.s_halo)
                 with torch.cuda.stream(self.s_main):
                     self.s_main.wait_event(self.ev_halo)              # edge rows + halo of the previous step
-                    s.step_region(_capi.LBM_REGION_INTERIOR, wm, self.s_main.cuda_stream)
+                    region(_capi.LBM_REGION_INTERIOR, wm, self.s_main.cuda_stream)
                     new_main = torch.cuda.Event()
                     new_main.record(self.s_main)
                 self.ev_halo, self.ev_main = new_halo, new_main
             else:
                 with torch.cuda.stream(self.s_main):
-                    s.step_region(_capi.LBM_REGION_ALL, wm, self.s_main.cuda_stream)
+                    region(_capi.LBM_REGION_ALL, wm, self.s_main.cuda_stream)
                     for w in self.halo.exchange(dst):
                         w.wait()
-            s.swap()
-            self.steps_done += 1
+            if two:
+                s.swap2()
+            else:
+                s.swap()
+            i += n
+            self.steps_done += n
 
     def sync(self) -> None:
         self.s_main.synchronize()

@@ -153,6 +153,16 @@ class CavitySolver:
     def swap(self) -> None:
         _capi.check(self._lib.lbm_swap(self._h))
 
+    def step2_available(self) -> bool:
+        """True if the two-step (temporal blocking) kernel can advance this handle right now."""
+        return bool(self._lib.lbm_step2_available(self._h))
+
+    def step2_region(self, region: int, write_macros: bool = False, stream: int = 0) -> None:
+        _capi.check(self._lib.lbm_step2_region(self._h, int(region), int(bool(write_macros)), C.c_void_p(stream)))
+
+    def swap2(self) -> None:
+        _capi.check(self._lib.lbm_swap2(self._h))
+
     def buffer_ptr(self, which: int) -> int:
         p = C.c_void_p()
         _capi.check(self._lib.lbm_buffer_ptr(self._h, int(which), C.byref(p)))

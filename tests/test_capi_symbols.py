@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_config_struct_matches_header_size():
     from latticeboltzmannsimulations_b200 import _capi
     assert ctypes.sizeof(_capi.Config) == 12 * 4 + 2 * 8
-    assert ctypes.sizeof(_capi.Layout) == 6 * 8
+    assert ctypes.sizeof(_capi.Layout) == 7 * 8
 
 
 def test_argument_validation_without_gpu():
@@ -43,7 +43,7 @@ def test_argument_validation_without_gpu():
     assert b"nx" in lib.lbm_last_error()
     cfg.nx = 100
     assert lib.lbm_state_bytes(ctypes.byref(cfg), ctypes.byref(n)) == 0
-    assert n.value == 9 * (64 + 2) * 128 * 8          # pitch rounded up to 128, one ghost row each side
+    assert n.value == (9 * (64 + 2) + 6) * 128 * 8    # pitch 128, one ghost row each side, + the 6-row ghost2 tail
 
 
 def test_no_cpu_fallback():

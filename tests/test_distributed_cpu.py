@@ -33,19 +33,34 @@ def test_halo_plan_is_symmetric():
     plans = [halo_plan(r, world, nyl) for r in range(world)]
     assert len(plans[0]) == 6 and len(plans[1]) == 12 and len(plans[3]) == 6
     for r in range(world):
-        for kind, peer, k, row in plans[r]:
+        for kind, peer, (what, k, row) in plans[r]:
             if kind != "send":
                 continue
             going_up = peer == r - 1
-            assert k in (UP_POPS if going_up else DOWN_POPS)
+            assert what == "row" and k in (UP_POPS if going_up else DOWN_POPS)
             assert row == (1 if going_up else nyl)
             want_row = nyl + 1 if going_up else 0
-            assert ("recv", r, k, want_row) in plans[peer]
+            assert ("recv", r, ("row", k, want_row)) in plans[peer]
     # order of sends on one side matches order of recvs on the other (NCCL/gloo match P2P ops in issue order)
     for r in range(world - 1):
-        down = [k for kind, peer, k, _ in plans[r] if kind == "send" and peer == r + 1]
-        up_recv = [k for kind, peer, k, _ in plans[r + 1] if kind == "recv" and peer == r]
+        down = [spec[1] for kind, peer, spec in plans[r] if kind == "send" and peer == r + 1]
+        up_recv = [spec[1] for kind, peer, spec in plans[r + 1] if kind == "recv" and peer == r]
         assert down == up_recv
+    # deep plan (two-step kernel): nine rows per direction, the shallow rows are a subset, same send/recv order
+    deep = [halo_plan(r, world, nyl, deep=True) for r in range(world)]
+    assert len(deep[0]) == 18 and len(deep[1]) == 36
+    for r in range(world):
+        for item in plans[r]:
+            assert item in deep[r]
+    for r in range(world - 1):
+        s_down = [spec for kind, peer, spec in deep[r] if kind == "send" and peer == r + 1]
+        r_up = [spec for kind, peer, spec in deep[r + 1] if kind == "recv" and peer == r]
+        assert [sp[1] for sp in s_down[:6]] == [sp[1] for sp in r_up[:6]] == [0, 1, 3, 4, 7, 8]
+        assert [sp[2] for sp in s_down[6:]] == [nyl - 1] * 3 and [sp[0] for sp in r_up[6:]] == ["g2"] * 3
+        s_up = [spec for kind, peer, spec in deep[r + 1] if kind == "send" and peer == r]
+        r_down = [spec for kind, peer, spec in deep[r] if kind == "recv" and peer == r + 1]
+        assert [sp[1] for sp in s_up[:6]] == [sp[1] for sp in r_down[:6]] == [0, 1, 3, 2, 5, 6]
+        assert [sp[2] for sp in s_up[6:]] == [2] * 3 and [(sp[0], sp[1]) for sp in r_down[6:]] == [("g2", 1)] * 3
 
 
 def test_shard_indices():
@@ -62,7 +77,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, nx, ny, steps, q):
+def _worker(rank, world, port, nx, ny, steps, q, deep=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -73,7 +88,8 @@ def _worker(rank, world, port, nx, ny, steps, q):
         ss = O.StripState.from_fin(fin0, p, y0, nyl)
         pitch = (nx + 31) // 32 * 32
         bufs = [torch.zeros(9, nyl + 2, pitch, dtype=torch.float64) for _ in range(2)]   # device layout [k][row][x]
-        ex = HaloExchanger(bufs, nx, rank, world)
+        g2 = [torch.zeros(2, 3, pitch, dtype=torch.float64) for _ in range(2)]           # second ghost rows
+        ex = HaloExchanger(list(zip(bufs, g2)), nx, rank, world, deep=deep)
         which = 0
         for _ in range(steps):
             ss.g[:, :, 0] = np.nan; ss.g[:, :, nyl + 1] = np.nan       # ghosts must come from the exchange only
@@ -96,13 +112,13 @@ def _worker(rank, world, port, nx, ny, steps, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nx,ny", [(2, 24, 30), (3, 20, 23)])
-def test_strip_decomposition_gloo(world, nx, ny):
+@pytest.mark.parametrize("world,nx,ny,deep", [(2, 24, 30, False), (3, 20, 23, True)])
+def test_strip_decomposition_gloo(world, nx, ny, deep):
     steps = 12
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, ny, steps, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nx, ny, steps, q, deep)) for r in range(world)]
     for pr in procs:
         pr.start()
     f, rho = q.get(timeout=120)

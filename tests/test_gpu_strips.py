@@ -13,48 +13,51 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run_strips_one_gpu(nx, ny, world, Re, steps, dtype, split_regions):
+def _run_strips_one_gpu(nx, ny, world, Re, steps, dtype, split_regions, two_step=True):
     import torch
     import latticeboltzmannsimulations_b200 as L
     from latticeboltzmannsimulations_b200 import _capi
-    from latticeboltzmannsimulations_b200.distributed import halo_plan, partition_rows
+    from latticeboltzmannsimulations_b200.distributed import exchange_local, halo_plan, partition_rows, strip_views
     tdt = torch.float64 if dtype == "float64" else torch.float32
     parts = partition_rows(ny, world)
-    solvers, bufs = [], []
+    deep = all(n >= 2 for _, n in parts)
+    solvers, views, ptrs = [], [], []
     for (y0, nyl) in parts:
         nbytes = L.CavitySolver.state_bytes(nx, ny, 1, dtype, ny_local=nyl)
         raw = [torch.zeros(nbytes // tdt.itemsize, dtype=tdt, device="cuda") for _ in range(2)]
         s = L.CavitySolver(nx, ny, 1, dtype, "MRT", y0=y0, ny_local=nyl, ext_buffers=[t.data_ptr() for t in raw])
         s.set_reynolds(Re)
         s.init_equilibrium()
-        lay = s.layout
         solvers.append(s)
-        bufs.append(([t.view(9, int(lay.rows), int(lay.pitch)) for t in raw], {raw[0].data_ptr(): 0, raw[1].data_ptr(): 1}))
-    for it in range(steps):
-        dst = [bufs[r][1][solvers[r].buffer_ptr(1)] for r in range(world)]
-        wm = it == steps - 1
+        views.append([strip_views(t, s.layout) for t in raw])
+        ptrs.append({raw[0].data_ptr(): 0, raw[1].data_ptr(): 1})
+    plans = [halo_plan(r, world, parts[r][1], deep) for r in range(world)]
+    it, used_two = 0, 0
+    while it < steps:
+        two = two_step and deep and steps - it >= 2 and all(s.step2_available() for s in solvers)
+        n = 2 if two else 1
+        wm = it + n == steps
+        dst = [ptrs[r][solvers[r].buffer_ptr(1)] for r in range(world)]
         for r, s in enumerate(solvers):
+            region = s.step2_region if two else s.step_region
             if split_regions and parts[r][1] >= 3:
-                s.step_region(_capi.LBM_REGION_EDGE, wm)
-                s.step_region(_capi.LBM_REGION_INTERIOR, wm)
+                region(_capi.LBM_REGION_EDGE, wm)
+                region(_capi.LBM_REGION_INTERIOR, wm)
             else:
-                s.step_region(_capi.LBM_REGION_ALL, wm)
+                region(_capi.LBM_REGION_ALL, wm)
         torch.cuda.synchronize()
-        for r in range(world):
-            for kind, peer, k, row in halo_plan(r, world, parts[r][1]):
-                if kind != "send":
-                    continue
-                ghost = parts[peer][1] + 1 if peer == r - 1 else 0
-                bufs[peer][0][dst[peer]][k, ghost, :nx] = bufs[r][0][dst[r]][k, row, :nx]
+        exchange_local(plans, [views[r][dst[r]] for r in range(world)], nx)
         torch.cuda.synchronize()
         for s in solvers:
-            s.swap()
+            s.swap2() if two else s.swap()
+        it += n
+        used_two += int(two)
     rho = np.concatenate([s.macros()[0] for s in solvers], axis=1)
     u = np.concatenate([s.macros()[1] for s in solvers], axis=2)
     f = np.concatenate([s.download_f() for s in solvers], axis=2)
     for s in solvers:
         s.close()
-    return rho, u, f
+    return rho, u, f, used_two
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
@@ -64,7 +67,26 @@ def test_strips_equal_single_domain_bitwise(nx, ny, world, split, dtype):
     steps = 60
     want = L.run_cavity(nx, ny, 1000, steps=steps, dtype=dtype, return_f=True)
     got = _run_strips_one_gpu(nx, ny, world, 1000, steps, dtype, split)
-    for a, b in zip(got, want):
+    for a, b in zip(got[:3], want):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("nx,ny,world,split,steps", [(1100, 640, 2, True, 9), (900, 700, 3, True, 12), (1500, 410, 4, False, 7),
+                                                      (800, 800, 5, True, 10)])
+def test_two_step_kernel_on_strips_bitwise(nx, ny, world, split, steps, dtype):
+    """Temporal blocking on y-strips (cavities above the size threshold of the two-step kernel): edge / interior
+    bands of whole tile rows, nine-row halo exchange, odd step counts -- bit-identical to the undecomposed run and
+    to the one-step kernels."""
+    import latticeboltzmannsimulations_b200 as L
+    want = L.run_cavity(nx, ny, 1000, steps=steps, dtype=dtype, return_f=True)
+    got = _run_strips_one_gpu(nx, ny, world, 1000, steps, dtype, split)
+    assert got[3] >= (steps - 1) // 2                      # the two-step kernel really ran
+    for a, b in zip(got[:3], want):
+        assert np.array_equal(a, b)
+    one = _run_strips_one_gpu(nx, ny, world, 1000, steps, dtype, split, two_step=False)
+    assert one[3] == 0
+    for a, b in zip(one[:3], want):
         assert np.array_equal(a, b)
 
 
@@ -110,6 +132,7 @@ def test_no_out_of_bounds_writes_canary(dtype):
         torch.cuda.synchronize()
         for r in raw:
             assert bool((r[:guard] == sentinel).all()) and bool((r[guard + n:] == sentinel).all())
-            body = r[guard:guard + n].view(9, int(lay.rows), int(lay.pitch))
+            from latticeboltzmannsimulations_b200.distributed import strip_views
+            body, g2 = strip_views(r[guard:guard + n], lay)
             assert bool((body[:, :, nx:] == 0).all())            # pitch padding never written
-            assert bool(torch.isfinite(body).all())
+            assert bool(torch.isfinite(body).all()) and bool((g2 == 0).all())
