@@ -179,6 +179,7 @@ class StripCavity:
             self.ev_main.record(torch.cuda.current_stream())
             self.ev_halo.record(torch.cuda.current_stream())
         self.steps_done = 0
+        self.passes_done = 0          # launches of the whole strip (a two-step pass counts once)
 
     def _dst_index(self) -> int:
         return self._ptr[self.solver.buffer_ptr(1)]
@@ -220,6 +221,7 @@ class StripCavity:
                 s.swap()
             i += n
             self.steps_done += n
+            self.passes_done += 1
 
     def sync(self) -> None:
         self.s_main.synchronize()
