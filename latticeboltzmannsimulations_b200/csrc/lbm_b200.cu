@@ -342,7 +342,7 @@ template <typename T, int TX_, int TY_> struct Fused2Cfg {
     static constexpr size_t SMEM = (size_t)(9 * PLANE + RX + 4) * sizeof(T);
 };
 
-template <typename T, int COLL, bool MACROS, int TX_, int TY_, int MINB>
+template <typename T, int COLL, bool MACROS, int TX_, int TY_, int MINB, bool GHOST2>
 __global__ void __launch_bounds__(256, MINB) lbm_step_fused2(const StepArgs a) {
     using Cfg = Fused2Cfg<T, TX_, TY_>;
     extern __shared__ __align__(16) unsigned char fused_smem[];
@@ -372,7 +372,8 @@ __global__ void __launch_bounds__(256, MINB) lbm_step_fused2(const StepArgs a) {
         if (x < 0 || x >= a.nx || y < 0 || y >= a.ny || yl > a.nyl) continue;
         const bool left = (x == 0), right = (x == a.nx - 1), lid = (y == 0), bot = (y == a.ny - 1);
         const long long rc = (long long)(yl + 1) * a.pitch + x, ru = rc - a.pitch, rd = rc + a.pitch;
-        const bool up2 = (yl == -1), dn2 = (yl == a.nyl);            // row above / below comes from the second ghost row
+        // row above / below comes from the second ghost row (edge bands of a y-strip only: GHOST2)
+        const bool up2 = GHOST2 && (yl == -1), dn2 = GHOST2 && (yl == a.nyl);
         T f[9];
         f[0] = src[rc];
         f[1] = left ? (T)0 : src[1 * P + rc - 1];
@@ -991,17 +992,17 @@ static bool fused2_capable(const lbm_solver* s) {
 static bool fused2_usable(const lbm_solver* s) { return fused2_capable(s) && s->nyl == s->cfg.ny; }
 
 // ---- fused two-step launch ------------------------------------------------------------------------------------
-template <typename T, int COLL, int TX, int TY, int MINB>
-static cudaError_t launch_fused2_tile(lbm_solver* s, const StepArgs& a, bool macros, cudaStream_t st) {
+template <typename T, int COLL, int TX, int TY, int MINB, bool GHOST2>
+static cudaError_t launch_fused2_cfg(lbm_solver* s, const StepArgs& a, bool macros, cudaStream_t st) {
     using Cfg = Fused2Cfg<T, TX, TY>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(lbm_step_fused2<T, COLL, false, TX, TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(lbm_step_fused2<T, COLL, true, TX, TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(lbm_step_fused2<T, COLL, false, TX, TY, MINB, GHOST2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(lbm_step_fused2<T, COLL, true, TX, TY, MINB, GHOST2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    // a.row_begin / a.row_count arrive in LOCAL ROWS (multiples of the tile height, see fused2_bands): convert
+    // a.row_begin / a.row_count arrive in LOCAL ROWS (multiples of the tile height, see lbm_step2_region): convert
     StepArgs t = a;
     t.row_begin = a.row_begin / Cfg::TY;
     const int tile_rows = (a.row_count + Cfg::TY - 1) / Cfg::TY;
@@ -1012,8 +1013,17 @@ static cudaError_t launch_fused2_tile(lbm_solver* s, const StepArgs& a, bool mac
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = s->use_pdl ? 1 : 0;
-    if (macros) return cudaLaunchKernelEx(&cfg, lbm_step_fused2<T, COLL, true, TX, TY, MINB>, t);
-    return cudaLaunchKernelEx(&cfg, lbm_step_fused2<T, COLL, false, TX, TY, MINB>, t);
+    if (macros) return cudaLaunchKernelEx(&cfg, lbm_step_fused2<T, COLL, true, TX, TY, MINB, GHOST2>, t);
+    return cudaLaunchKernelEx(&cfg, lbm_step_fused2<T, COLL, false, TX, TY, MINB, GHOST2>, t);
+}
+
+template <typename T, int COLL, int TX, int TY, int MINB>
+static cudaError_t launch_fused2_tile(lbm_solver* s, const StepArgs& a, bool macros, cudaStream_t st) {
+    // only a band that contains the first or last row of a strip that is not the whole cavity reads ghost2
+    const bool strip = s->nyl != s->cfg.ny;
+    const bool touches_end = a.row_begin == 0 || a.row_begin + a.row_count >= s->nyl;
+    if (strip && touches_end) return launch_fused2_cfg<T, COLL, TX, TY, MINB, true>(s, a, macros, st);
+    return launch_fused2_cfg<T, COLL, TX, TY, MINB, false>(s, a, macros, st);
 }
 
 template <typename T, int COLL>
@@ -1025,9 +1035,6 @@ static cudaError_t launch_fused2_t(lbm_solver* s, const StepArgs& a, bool macros
         case 2: return launch_fused2_tile<T, COLL, 32, 16, 3>(s, a, macros, st);
         case 3: return launch_fused2_tile<T, COLL, 64, 8, 4>(s, a, macros, st);
         case 4: return launch_fused2_tile<T, COLL, 32, 16, 4>(s, a, macros, st);
-        case 5: return launch_fused2_tile<T, COLL, 64, 12, 3>(s, a, macros, st);
-        case 6: return launch_fused2_tile<T, COLL, 32, 16, 5>(s, a, macros, st);
-        case 7: return launch_fused2_tile<T, COLL, 32, 8, 6>(s, a, macros, st);
         default: return launch_fused2_tile<T, COLL, 64, 16, 2>(s, a, macros, st);
     }
 }
@@ -1036,8 +1043,7 @@ static cudaError_t launch_fused2_t(lbm_solver* s, const StepArgs& a, bool macros
 static int fused2_tile_height(const lbm_solver* s) {
     const int variant = s->fused2_tile >= 0 ? s->fused2_tile : (s->esz == 8 ? 3 : 4);
     switch (variant) {
-        case 1: case 3: case 7: return 8;
-        case 5: return 12;
+        case 1: case 3: return 8;
         default: return 16;
     }
 }

@@ -159,6 +159,24 @@ def test_batch_equals_standalone():
     assert np.array_equal(feq0, O.init_fields(64, 48, 0.08)[2])
 
 
+def test_two_step_kernel_batched_and_against_oracle():
+    """Temporal blocking with several cavities per launch (per-cavity lid density / corner carries): each cavity of a
+    batch that is large enough for the two-step kernel equals its standalone run (small enough to take the one-step
+    path) bit for bit; and a single large cavity matches the oracle."""
+    import latticeboltzmannsimulations_b200 as L
+    Re = [100.0, 1000.0, 5000.0, 400.0]
+    f_final, u_final, _, _ = L.datagen(Re, 512, 300, steps=41, collision="MRT", dtype="float64")      # 614 400 nodes
+    for b, r in enumerate(Re):
+        rho, u, f = L.run_cavity(512, 300, r, steps=41, collision="MRT", dtype="float64", return_f=True)
+        assert np.array_equal(f, f_final[b]) and np.array_equal(u, u_final[b])
+    nx, ny, n = 900, 700, 60
+    p = O.Params(nx, ny, Re=2000, collision="MRT")
+    want = O.run_fast(p, n)
+    for dtype in ("float64", "float32"):
+        got = L.run_cavity(nx, ny, 2000, steps=n, dtype=dtype, return_f=True)
+        assert_close(got, want, dtype, what="two-step 900x700")
+
+
 def test_split_runs_and_reupload_are_bit_identical():
     """steps(a) ; steps(b) == steps(a+b), and download -> upload -> continue changes nothing (fp64, bit exact)."""
     import latticeboltzmannsimulations_b200 as L
@@ -414,12 +432,16 @@ def test_kernel_variants_are_bit_identical(env, monkeypatch):
     """Every compiled data-movement variant (scalar / 2 / 4 nodes per thread, with and without graphs and programmatic
     dependent launch) produces the same bits as the default configuration."""
     import latticeboltzmannsimulations_b200 as L
-    cases = [("float64", 200, 90, "MRT", False), ("float32", 131, 77, "SRT", False), ("float32", 96, 64, "MRT", True)]
-    ref = [L.run_cavity(nx, ny, 1000, steps=70, dtype=dt, collision=c, turb=t, return_f=True) for dt, nx, ny, c, t in cases]
+    # the last three are above the size threshold of the two-step (temporal blocking) kernel; 70 and 71 steps end on
+    # a macro-writing two-step launch and on a one-step launch respectively
+    cases = [("float64", 200, 90, "MRT", False), ("float32", 131, 77, "SRT", False), ("float32", 96, 64, "MRT", True),
+             ("float64", 1000, 640, "MRT", False), ("float32", 1100, 600, "SRT", False), ("float64", 777, 801, "TRT", False)]
+    ref = [L.run_cavity(nx, ny, 1000, steps=70 + (nx == 777), dtype=dt, collision=c, turb=t, return_f=True)
+           for dt, nx, ny, c, t in cases]
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     for (dt, nx, ny, c, t), want in zip(cases, ref):
-        got = L.run_cavity(nx, ny, 1000, steps=70, dtype=dt, collision=c, turb=t, return_f=True)
+        got = L.run_cavity(nx, ny, 1000, steps=70 + (nx == 777), dtype=dt, collision=c, turb=t, return_f=True)
         for a, b in zip(got, want):
             assert np.array_equal(a, b), (env, dt, c)
 

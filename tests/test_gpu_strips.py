@@ -81,7 +81,8 @@ def test_two_step_kernel_on_strips_bitwise(nx, ny, world, split, steps, dtype):
     import latticeboltzmannsimulations_b200 as L
     want = L.run_cavity(nx, ny, 1000, steps=steps, dtype=dtype, return_f=True)
     got = _run_strips_one_gpu(nx, ny, world, 1000, steps, dtype, split)
-    assert got[3] >= (steps - 1) // 2                      # the two-step kernel really ran
+    if dtype == "float64" or nx >= 1024:                  # (fp32 takes it for wide cavities only)
+        assert got[3] >= (steps - 1) // 2                  # the two-step kernel really ran
     for a, b in zip(got[:3], want):
         assert np.array_equal(a, b)
     one = _run_strips_one_gpu(nx, ny, world, 1000, steps, dtype, split, two_step=False)
