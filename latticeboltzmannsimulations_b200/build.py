@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "liblbm_b200.so")
 SOURCES = ["lbm_b200.cu"]
-HEADERS = ["lbm_device.cuh", os.path.join("..", "..", "include", "lbm_b200.h")]
+HEADERS = ["lbm_device.cuh", "lbm_kernels.cuh", "lbm_fused2.cuh", "lbm_tma.cuh",
+           os.path.join("..", "..", "include", "lbm_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-shared"]
