@@ -42,6 +42,14 @@ static int fail(int code, const std::string& msg) {
                         std::string(#call) + ": " + cudaGetErrorString(e__));                            \
     } while (0)
 
+// Where temporal blocking pays (tools/small_grid.py, tools/fused2_check.py, fp64): large cavities with 64x8 tiles
+// (1024^2: 45 807 -> 63 586 MLUPS, 4096^2: 47 558 -> 74 393); launch-latency-bound small cavities with 32x8 tiles, so
+// that one wave still covers all SMs (384^2: 3.46 -> 2.98 us/step, 128^2: 2.11 -> 1.97).  In between (640^2:
+// 6.23 vs 6.65 us/step) neither tile shape fills the machine well and the one-step kernel stays.
+#define LBM_FUSED2_MIN_NODES 10000
+#define LBM_FUSED2_SMALL_NODES 250000     // below: 32x8 tiles
+#define LBM_FUSED2_LARGE_NODES 600000     // from here: 64x8 (fp64) / 32x16 (fp32) tiles
+
 // ------------------------------------------------------------------------------------------------------------
 // solver object
 // ------------------------------------------------------------------------------------------------------------
@@ -91,6 +99,7 @@ struct lbm_solver {
     int use_fused2 = 1;        // temporal blocking (two steps per launch) for whole cavities
     int side = 0;              // which half of the double-buffered rho_lid / carry arrays is current
     int fused2_tile = -1;      // tile-shape variant of the fused kernel (-1 = per-dtype default)
+    long long fused2_min_nodes = LBM_FUSED2_MIN_NODES;
 };
 
 // A fresh state (init / upload) un-freezes every cavity; graphs captured with the old flag pointer are dropped.
@@ -326,20 +335,27 @@ static void launch_vec_coll(int coll, const StepArgs& a, const Launch& L, bool m
     }
 }
 
-// Below this many nodes the 64x8 / 32x16 tiles no longer fill the 148 SMs several times over and the one-step kernel
-// (one wave of dependent L2 loads) is as fast or faster: 384^2 3.6 vs 3.9 us/step, 640^2 equal, 1024^2 46 -> 64 GLUPS.
-#define LBM_FUSED2_MIN_NODES 600000
-
 // Temporal blocking applies to this handle at all (whole cavity or y-strip of at least two rows)?
 static bool fused2_capable(const lbm_solver* s) {
     // fp32 gains less from it (it is ALU- rather than HBM-bound) and loses on narrow cavities: 8 x 32 cavities of 384^2
     // ran at 666 537 MLUPS with it against 690 216 without
     if (s->esz == 4 && s->cfg.nx < 1024) return false;
-    return s->use_fused2 && (long long)s->cfg.nx * s->cfg.ny * s->cfg.batch >= LBM_FUSED2_MIN_NODES && s->nyl >= 2 &&
+    const long long nodes = (long long)s->cfg.nx * s->cfg.ny * s->cfg.batch;
+    if (s->fused2_tile < 0 && nodes >= LBM_FUSED2_SMALL_NODES && nodes < LBM_FUSED2_LARGE_NODES) return false;
+    return s->use_fused2 && nodes >= s->fused2_min_nodes && s->nyl >= 2 &&
            !s->cfg.turb && s->engine == LBM_ENGINE_LDG && !s->active && s->cfg.semantics == LBM_SEMANTICS_C;
 }
 // ... and to lbm_step, which owns whole cavities only
 static bool fused2_usable(const lbm_solver* s) { return fused2_capable(s) && s->nyl == s->cfg.ny; }
+
+// Tile-shape variant of the two-step kernel.  Defaults from tools/fused2_sweep.py at 4096^2: fp64 64x8 tiles at
+// 4 CTAs/SM, fp32 32x16; cavities small enough to be launch-latency-bound take 32x8 tiles so that one wave still
+// covers all SMs (384^2 -> 576 CTAs).
+static int fused2_variant(const lbm_solver* s) {
+    if (s->fused2_tile >= 0) return s->fused2_tile;
+    if ((long long)s->cfg.nx * s->cfg.ny * s->cfg.batch < LBM_FUSED2_SMALL_NODES) return 9;
+    return s->esz == 8 ? 3 : 4;
+}
 
 // ---- fused two-step launch ------------------------------------------------------------------------------------
 template <typename T, int COLL, int TX, int TY, int MINB, bool GHOST2>
@@ -374,9 +390,9 @@ static cudaError_t launch_fused2_tile(lbm_solver* s, const StepArgs& a, bool mac
 
 template <typename T, int COLL>
 static cudaError_t launch_fused2_t(lbm_solver* s, const StepArgs& a, bool macros, cudaStream_t st) {
-    // defaults from tools/fused2_sweep.py at 4096^2: fp64 64x8 tiles at 4 CTAs/SM (73 610 MLUPS), fp32 32x16 at 4 CTAs/SM (105 000-113 000)
-    const int variant = s->fused2_tile >= 0 ? s->fused2_tile : (sizeof(T) == 8 ? 3 : 4);
+    const int variant = fused2_variant(s);
     switch (variant) {
+        case 9: return launch_fused2_tile<T, COLL, 32, 8, 4>(s, a, macros, st);
         case 1: return launch_fused2_tile<T, COLL, 64, 8, 3>(s, a, macros, st);
         case 2: return launch_fused2_tile<T, COLL, 32, 16, 3>(s, a, macros, st);
         case 3: return launch_fused2_tile<T, COLL, 64, 8, 4>(s, a, macros, st);
@@ -387,9 +403,8 @@ static cudaError_t launch_fused2_t(lbm_solver* s, const StepArgs& a, bool macros
 
 // Tile height of the fused kernel in use (needed to cut a strip into edge / interior bands of whole tile rows).
 static int fused2_tile_height(const lbm_solver* s) {
-    const int variant = s->fused2_tile >= 0 ? s->fused2_tile : (s->esz == 8 ? 3 : 4);
-    switch (variant) {
-        case 1: case 3: return 8;
+    switch (fused2_variant(s)) {
+        case 1: case 3: case 9: return 8;
         default: return 16;
     }
 }
@@ -595,6 +610,7 @@ int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
     if (const char* ev = getenv("LBM_B200_PDL")) s->use_pdl = atoi(ev) != 0;
     if (const char* ev = getenv("LBM_B200_FUSED2")) s->use_fused2 = atoi(ev) != 0;
     if (const char* ev = getenv("LBM_B200_FUSED2_TILE")) s->fused2_tile = atoi(ev);
+    if (const char* ev = getenv("LBM_B200_FUSED2_MIN_NODES")) s->fused2_min_nodes = atoll(ev);
     if (const char* ev = getenv("LBM_B200_TMA_VARIANT")) s->tma_variant = atoi(ev) % LBM_TMA_VARIANTS;
     if (const char* ev = getenv("LBM_B200_TMA_CTAS")) s->tma_ctas_per_sm = atoi(ev) > 0 ? atoi(ev) : 1;
 #define CKD(call)                                                                       \
