@@ -33,7 +33,8 @@ enum lbm_status { LBM_OK = 0, LBM_EINVAL = 1, LBM_ECUDA = 2, LBM_ENOMEM = 3, LBM
 enum lbm_dtype { LBM_F32 = 0, LBM_F64 = 1 };
 /* `RT` of MRT_GPU.py:48 */
 enum lbm_collision { LBM_SRT = 0, LBM_TRT = 1, LBM_MRT = 2 };
-/* which rows of the local strip a launch covers (multi-GPU overlap of halo exchange and interior) */
+/* which rows of the local strip a launch covers (multi-GPU overlap of halo exchange and interior): EDGE = the first
+ * two and last two rows (the rows a halo exchange ships), INTERIOR = the rest, ALL = both */
 enum lbm_region { LBM_REGION_ALL = 0, LBM_REGION_EDGE = 1, LBM_REGION_INTERIOR = 2 };
 /* which reference variant the step reproduces: C = MRT_GPU.py (push + NEBB in funBC; the product
  * path), A = MRT.py (NumPy solver: SRT only, slice streaming with the exclusive xsize_max bound that leaves the

@@ -484,18 +484,22 @@ static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin,
     return LBM_OK;
 }
 
+// Row bands of a one-step region launch.  EDGE = the first TWO and the last TWO rows of the strip: the halo exchange
+// that follows an EDGE launch (while INTERIOR is still running) ships rows 0, 1, nyl-2 and nyl-1 -- the second ones
+// feed the neighbour's second ghost rows for the two-step kernel -- so all four must be complete by then.
 static int region_rows(lbm_solver* s, int region, int rows[2][3], int* n) {
     // rows[i] = {begin, count, stride}
     const int nyl = s->nyl;
     *n = 0;
-    if (region == LBM_REGION_ALL) {
+    const bool split = nyl >= 5;            // otherwise the edge bands are the whole strip
+    if (region == LBM_REGION_ALL || (region == LBM_REGION_EDGE && !split)) {
         rows[0][0] = 0; rows[0][1] = nyl; rows[0][2] = 1; *n = 1;
     } else if (region == LBM_REGION_EDGE) {
-        if (nyl == 1) { rows[0][0] = 0; rows[0][1] = 1; rows[0][2] = 1; }
-        else { rows[0][0] = 0; rows[0][1] = 2; rows[0][2] = nyl - 1; }
-        *n = 1;
+        rows[0][0] = 0; rows[0][1] = 2; rows[0][2] = 1;
+        rows[1][0] = nyl - 2; rows[1][1] = 2; rows[1][2] = 1;
+        *n = 2;
     } else if (region == LBM_REGION_INTERIOR) {
-        rows[0][0] = 1; rows[0][1] = nyl - 2; rows[0][2] = 1; *n = 1;
+        if (split) { rows[0][0] = 2; rows[0][1] = nyl - 4; rows[0][2] = 1; *n = 1; }
     } else {
         return fail(LBM_EINVAL, "bad region");
     }

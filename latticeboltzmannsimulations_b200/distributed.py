@@ -170,7 +170,7 @@ class StripCavity:
         # the deep plan (what the two-step kernel needs) whenever every strip has at least two rows
         self.deep = all(n >= 2 for _, n in self.parts)
         self.halo = HaloExchanger(self.buffers, nx, self.rank, self.world, group, deep=self.deep)
-        self.overlap = overlap and self.nyl >= 3
+        self.overlap = overlap and self.nyl >= 5
         with torch.cuda.device(self.device):
             self.s_main = torch.cuda.Stream()
             self.s_halo = torch.cuda.Stream(priority=-1)

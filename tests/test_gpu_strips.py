@@ -38,16 +38,20 @@ def _run_strips_one_gpu(nx, ny, world, Re, steps, dtype, split_regions, two_step
         n = 2 if two else 1
         wm = it + n == steps
         dst = [ptrs[r][solvers[r].buffer_ptr(1)] for r in range(world)]
-        for r, s in enumerate(solvers):
+        # worst-case ordering of the overlapped multi-GPU step: EDGE bands of every rank, then the halo exchange,
+        # and only then the INTERIOR bands -- rows the exchange ships must already be final after EDGE
+        do_split = split_regions and all(n >= 5 for _, n in parts)
+        for s in solvers:
             region = s.step2_region if two else s.step_region
-            if split_regions and parts[r][1] >= 3:
-                region(_capi.LBM_REGION_EDGE, wm)
-                region(_capi.LBM_REGION_INTERIOR, wm)
-            else:
-                region(_capi.LBM_REGION_ALL, wm)
+            region(_capi.LBM_REGION_EDGE if do_split else _capi.LBM_REGION_ALL, wm)
         torch.cuda.synchronize()
         exchange_local(plans, [views[r][dst[r]] for r in range(world)], nx)
         torch.cuda.synchronize()
+        if do_split:
+            for s in solvers:
+                region = s.step2_region if two else s.step_region
+                region(_capi.LBM_REGION_INTERIOR, wm)
+            torch.cuda.synchronize()
         for s in solvers:
             s.swap2() if two else s.swap()
         it += n
@@ -61,7 +65,8 @@ def _run_strips_one_gpu(nx, ny, world, Re, steps, dtype, split_regions, two_step
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
-@pytest.mark.parametrize("nx,ny,world,split", [(96, 64, 2, True), (50, 37, 3, True), (64, 32, 8, False), (40, 9, 4, True)])
+@pytest.mark.parametrize("nx,ny,world,split", [(96, 64, 2, True), (50, 37, 3, True), (64, 32, 8, False), (40, 9, 4, True),
+                                               (256, 192, 2, True), (200, 120, 4, True)])
 def test_strips_equal_single_domain_bitwise(nx, ny, world, split, dtype):
     import latticeboltzmannsimulations_b200 as L
     steps = 60
