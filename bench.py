@@ -301,8 +301,10 @@ def run_single_gpu(args):
         pass
     out = {"metric": "MLUPS", "value": round(r64["mlups"], 1), "unit": "MLUPS", "n_gpus": 1, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(r64["ms_per_step"], 5), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": wl, "description": desc, "collision": "MRT", "engine": r64["engine"],
+                      "scaling_note": "N > 1 runs ONE 32768^2 cavity in y-strips (strong scaling); its single-GPU anchor is "
+                                      "`--workload cavity32768` (74 944 MLUPS); MLUPS is size-independent at these sizes",
                       "l2": "state (2 x %.2f GB) far larger than the 126 MB L2: no flush needed" % (nx * ny * 72 / 1e9)},
            "roofline": {"bound": "hbm", "achieved": round(r64["gbs"], 1), "peak": peak, "unit": "GB/s",
                         "frac": round(r64["gbs"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
