@@ -176,7 +176,7 @@ def run_reference_arm(args, rank, world):
                     "threads) on a %dx%d sub-cavity of the workload" % (cores, n, n)}
     out = {"impl": "reference", "metric": "MLUPS", "value": round(mlups, 2), "unit": "MLUPS", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t / args.steps * 1e3, 4),
-           "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": wl, "description": desc, "sample_grid": [n, n]},
            "cpu_baseline": cb,
