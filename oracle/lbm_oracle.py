@@ -14,9 +14,12 @@ the upstream repo RaghuvirJonnagiri/LatticeBoltzmannSimulations):
   TRT ``:426-531`` and MRT ``:535-662`` forms, optional Smagorinsky ``:570-589``, then ``funBC``
   ``:664-699``), evaluated in fp64.  Pinned partially: moments, overrides, equilibrium, SRT collision
   and push streaming agree with the *compiled* reference ``functions.allfunc`` (``functions.pyx:45-222``)
-  to 2.2e-16 on one step (same tests).  The MRT relaxation and ``funBC`` are pinned only by reading
-  the cited lines -- the reference ships no tests and PyCUDA cannot run here: **parity unpinned**
-  for those two pieces, and every line below that restates them carries its citation.
+  to 2.2e-16 on one step (same tests).  The MRT relaxation and ``funBC`` cannot be executed on a CPU (PyCUDA kernel
+  strings); they are pinned on the GPU box instead: ``oracle/build_ref_kernels.py`` compiles the reference's own
+  ``funRT`` (SRT/TRT/MRT, +-Smagorinsky) and ``funBC`` strings with nvcc and
+  ``tests/test_gpu_reference_kernels.py`` runs them on the B200 against this oracle -- agreement at fp32 round-off
+  (rho 1e-6..5e-6, u 4e-6..1.8e-5 of uLB; the reference kernels are fp32), where any semantic slip would show at
+  1e-3..1e-2.  Every line below that restates those pieces carries its citation.
 
 ``step_C`` is the literal two-kernel push form.  ``PullState``/``step_C_pull`` is the same update
 re-expressed as the single fused *pull* pass that the CUDA kernel implements (state kept between steps
