@@ -8,11 +8,11 @@ It is a plain NumPy fp64 restatement of the reference's arithmetic (citations ar
 the upstream repo RaghuvirJonnagiri/LatticeBoltzmannSimulations):
 
 * semantics ``"A"``  -- the NumPy solver, ``MRT.py:286-453`` (SRT collision, slice streaming with the
-  exclusive ``xsize_max`` bound, "= feq" left wall).  Pinned: ``tests/test_oracle_vs_reference.py`` and
+  exclusive ``xsize_max`` bound, "= feq" left wall).  Pinned: ``tests/test_oracle.py`` and
   ``tests/golden/make_golden.py`` run the real ``MRT.py`` under import stubs and require a 0.0 difference.
 * semantics ``"C"``  -- the PyCUDA solver, ``MRT_GPU.py:336-703`` (``funRT`` in its SRT ``:338-422``,
   TRT ``:426-531`` and MRT ``:535-662`` forms, optional Smagorinsky ``:570-589``, then ``funBC``
-  ``:664-699``), evaluated in fp64.  Pinned partially: moments, overrides, equilibrium, SRT collision
+  ``:664-699``), evaluated in fp64.  Pinned in two parts: moments, overrides, equilibrium, SRT collision
   and push streaming agree with the *compiled* reference ``functions.allfunc`` (``functions.pyx:45-222``)
   to 2.2e-16 on one step (same tests).  The MRT relaxation and ``funBC`` cannot be executed on a CPU (PyCUDA kernel
   strings); they are pinned on the GPU box instead: ``oracle/build_ref_kernels.py`` compiles the reference's own
