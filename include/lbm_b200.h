@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LBM_B200_ABI_VERSION 2
+#define LBM_B200_ABI_VERSION 3
 
 enum lbm_status { LBM_OK = 0, LBM_EINVAL = 1, LBM_ECUDA = 2, LBM_ENOMEM = 3, LBM_ESTATE = 4 };
 enum lbm_dtype { LBM_F32 = 0, LBM_F64 = 1 };
@@ -88,6 +88,26 @@ int lbm_state_bytes(const lbm_config_t* cfg, size_t* bytes);
 int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out);
 int lbm_destroy(lbm_handle_t h);
 int lbm_get_layout(lbm_handle_t h, lbm_layout_t* out);
+
+/* Kernel-selection knobs.  None of them changes a result (every kernel family is bit-identical to every other,
+ * tests/test_gpu_parity.py::test_kernel_variants_are_bit_identical); they exist for the tuning tools under tools/ and
+ * for those tests.  The reference has no counterpart (its block shape is the literal of MRT_GPU.py:53-54).  Keys:
+ *   "two_step"            0 = one lattice step per launch only (default 1: temporal blocking where it pays)
+ *   "two_step_min_nodes"  smallest batch x nx x ny that uses a two-step kernel (default 10000)
+ *   "slide"               0 = never use the sliding-window two-step kernel (default 1)
+ *   "slide_min_nodes"     smallest batch x nx x ny that uses it instead of the shared-memory tiles (default 600000)
+ *   "slide_h"             rows per segment of the sliding-window kernel, 0 = automatic
+ *   "march"               0 = never use the marching two-step kernel (default 1; it serves turb = 1)
+ *   "march_min_nodes"     smallest batch x nx x ny that uses it (default 600000)
+ *   "march_variant"       compiled (nodes per lane, register budget) variant, 0 = shipped default
+ *   "march_h"             rows per segment, 0 = automatic
+ *   "tile"                tile shape of the shared-memory two-step kernel, -1 = automatic
+ *   "vec_f64", "vec_f32"  nodes per thread of the one-step kernels (1|2, 1|2|4)
+ *   "graph", "pdl"        CUDA graphs for small cavities / programmatic dependent launch (default 1, 1)
+ *   "tma_variant", "tma_ctas"   tile configuration and CTAs per SM of the optional TMA engine
+ * Unknown keys and out-of-range values return LBM_EINVAL.  The Python binding applies the comma-separated
+ * "key=value" list in the environment variable LBM_B200_TUNING to every handle it creates. */
+int lbm_set_tuning(lbm_handle_t h, const char* key, int64_t value);
 
 /* functions.pyx:38-43 set_omega(uLB, Re, ysize) / MRT_GPU.py:63-65: omega = 2 / (6 uLB ny / Re + 1); the other
  * MRT rates take the GPU-script values (omega_e 1.0, omega_eps = omega_q = 1.2, MRT_GPU.py:88-91) and the TRT

@@ -24,7 +24,7 @@ SEMANTICS = {"C": 0, "A": 1}
 # every symbol include/lbm_b200.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = [
     "lbm_last_error", "lbm_abi_version", "lbm_device_count", "lbm_state_bytes", "lbm_create", "lbm_destroy",
-    "lbm_get_layout", "lbm_set_reynolds", "lbm_set_rates", "lbm_init_equilibrium", "lbm_upload_f",
+    "lbm_get_layout", "lbm_set_tuning", "lbm_set_reynolds", "lbm_set_rates", "lbm_init_equilibrium", "lbm_upload_f",
     "lbm_download_f", "lbm_step", "lbm_step_region", "lbm_swap", "lbm_step2_region", "lbm_swap2", "lbm_step2_available", "lbm_buffer_ptr", "lbm_get_macros",
     "lbm_get_macros_current", "lbm_equilibrium", "lbm_mean_u", "lbm_set_active", "lbm_diagnostics", "lbm_sync", "lbm_get_counters", "lbm_engine_name",
 ]
@@ -56,19 +56,16 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("LBM_B200_LIB", LIB_PATH)        # development override (experimental builds)
-    if path != LIB_PATH:
-        lib = C.CDLL(path)
-    elif not os.path.exists(LIB_PATH):
+    from . import build as _build
+    if _build.stale():
+        # sources newer than the library (or no library): rebuild; a stale library that cannot be rebuilt is an
+        # error, never silently used -- parity tests and benchmarks must run the kernels in the tree
         try:
-            from . import build as _build
             _build.build()
         except Exception as exc:  # pragma: no cover - build container always has nvcc
-            raise ImportError("liblbm_b200.so is not built and could not be built (%s); run "
+            raise ImportError("liblbm_b200.so is missing or older than its sources and could not be built (%s); run "
                               "`python -m latticeboltzmannsimulations_b200.build`. There is no CPU fallback." % exc)
-        lib = C.CDLL(LIB_PATH)
-    else:
-        lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
     H = C.c_void_p
     lib.lbm_last_error.restype = C.c_char_p
     lib.lbm_last_error.argtypes = []
@@ -78,6 +75,7 @@ def load():
     lib.lbm_create.argtypes = [C.POINTER(Config), C.POINTER(H)]
     lib.lbm_destroy.argtypes = [H]
     lib.lbm_get_layout.argtypes = [H, C.POINTER(Layout)]
+    lib.lbm_set_tuning.argtypes = [H, C.c_char_p, C.c_int64]
     lib.lbm_set_reynolds.argtypes = [H, C.c_int, C.c_double, C.c_double]
     lib.lbm_set_rates.argtypes = [H, C.c_int] + [C.c_double] * 6
     lib.lbm_init_equilibrium.argtypes = [H]

@@ -22,9 +22,17 @@
 #include "lbm_device.cuh"
 #include "lbm_kernels.cuh"
 #include "lbm_fused2.cuh"
+#include "lbm_internal.h"
 #include "lbm_tma.cuh"
 
 using namespace lbm;
+
+namespace lbm {
+int march2_variants_f64(); int march2_cols_f64(int);
+int march2_variants_f32(); int march2_cols_f32(int);
+int march2_variants(int esz) { return esz == 8 ? march2_variants_f64() : march2_variants_f32(); }
+int march2_cols(int esz, int variant) { return esz == 8 ? march2_cols_f64(variant) : march2_cols_f32(variant); }
+}  // namespace lbm
 
 // ------------------------------------------------------------------------------------------------------------
 // error handling
@@ -49,6 +57,12 @@ static int fail(int code, const std::string& msg) {
 #define LBM_FUSED2_MIN_NODES 10000
 #define LBM_FUSED2_SMALL_NODES 250000     // below: 32x8 tiles
 #define LBM_FUSED2_LARGE_NODES 600000     // from here: 64x8 (fp64) / 32x16 (fp32) tiles
+// From here the marching two-step kernel (lbm_march2.cuh: one warp per x-strip segment, rolling register window)
+// replaces the shared-memory tiles; it also covers the Smagorinsky closure and batches with frozen cavities.
+#define LBM_MARCH_MIN_NODES 600000
+// The sliding-window two-step kernel (lbm_slide2.cuh: one CTA per column strip, cp.async double-buffered source rows)
+// takes over from the tiles at the same size; the marching kernel then only serves the Smagorinsky closure.
+#define LBM_SLIDE_MIN_NODES 600000
 
 // ------------------------------------------------------------------------------------------------------------
 // solver object
@@ -100,6 +114,13 @@ struct lbm_solver {
     int side = 0;              // which half of the double-buffered rho_lid / carry arrays is current
     int fused2_tile = -1;      // tile-shape variant of the fused kernel (-1 = per-dtype default)
     long long fused2_min_nodes = LBM_FUSED2_MIN_NODES;
+    int use_march = 1;         // marching two-step kernel for large cavities / batches
+    int march_variant = 0;     // compiled (nodes per lane, register budget) variant, 0 = shipped default
+    int march_h = 0;           // rows per segment, 0 = chosen from the number of work items
+    long long march_min_nodes = LBM_MARCH_MIN_NODES;
+    int use_slide = 1;         // sliding-window two-step kernel for large cavities / batches (no closure)
+    int slide_h = 0;           // rows per segment, 0 = chosen from the number of work items
+    long long slide_min_nodes = LBM_SLIDE_MIN_NODES;
 };
 
 // A fresh state (init / upload) un-freezes every cavity; graphs captured with the old flag pointer are dropped.
@@ -126,7 +147,13 @@ static StepArgs make_args(lbm_solver* s, const void* src, void* dst) {
     a.rho_lid_out = (char*)s->rho_lid + (s->side ^ 1) * rl_half;
     a.carry_out = (char*)s->carry + (s->side ^ 1) * ca_half;
     a.cav = s->cav;
-    a.pi_eq = s->pi_eq; a.rho_prev = s->rho_prev;
+    if (s->pi_eq) {   // Smagorinsky state, two halves like rho_lid: one-step kernels update the current half in place
+        const size_t m_half = (size_t)s->cfg.batch * s->mplane * s->esz;
+        a.pi_eq = (char*)s->pi_eq + s->side * m_half;
+        a.rho_prev = (char*)s->rho_prev + s->side * m_half;
+        a.pi_eq_out = (char*)s->pi_eq + (s->side ^ 1) * m_half;
+        a.rho_prev_out = (char*)s->rho_prev + (s->side ^ 1) * m_half;
+    }
     a.active = s->active;
     a.nx = s->cfg.nx; a.ny = s->cfg.ny; a.y0 = s->cfg.y0; a.nyl = s->nyl; a.pitch = s->pitch;
     a.plane = s->plane; a.cavity = s->cavity; a.mplane = s->mplane;
@@ -335,18 +362,51 @@ static void launch_vec_coll(int coll, const StepArgs& a, const Launch& L, bool m
     }
 }
 
-// Temporal blocking applies to this handle at all (whole cavity or y-strip of at least two rows)?
-static bool fused2_capable(const lbm_solver* s) {
-    // fp32 gains less from it (it is ALU- rather than HBM-bound) and loses on narrow cavities: 8 x 32 cavities of 384^2
-    // ran at 666 537 MLUPS with it against 690 216 without
-    if (s->esz == 4 && s->cfg.nx < 1024) return false;
+// Which two-step (temporal blocking) kernel advances this handle, if any (whole cavity or y-strip of >= 2 rows).
+enum { TWO_NONE = 0, TWO_TILE = 1, TWO_MARCH = 2, TWO_SLIDE = 3 };
+static int two_step_kind(const lbm_solver* s) {
+    if (!s->use_fused2 || s->engine != LBM_ENGINE_LDG || s->cfg.semantics != LBM_SEMANTICS_C || s->nyl < 2) return TWO_NONE;
     const long long nodes = (long long)s->cfg.nx * s->cfg.ny * s->cfg.batch;
-    if (s->fused2_tile < 0 && nodes >= LBM_FUSED2_SMALL_NODES && nodes < LBM_FUSED2_LARGE_NODES) return false;
-    return s->use_fused2 && nodes >= s->fused2_min_nodes && s->nyl >= 2 &&
-           !s->cfg.turb && s->engine == LBM_ENGINE_LDG && !s->active && s->cfg.semantics == LBM_SEMANTICS_C;
+    if (nodes < s->fused2_min_nodes) return TWO_NONE;
+    const bool whole = s->nyl == s->cfg.ny;
+    if (s->use_slide && nodes >= s->slide_min_nodes && !s->cfg.turb) return TWO_SLIDE;
+    // the closure's per-node state has no halo exchange: two-step with turb = 1 on whole cavities only
+    if (s->use_march && nodes >= s->march_min_nodes && (!s->cfg.turb || whole)) return TWO_MARCH;
+    // shared-memory tiles: no closure, no frozen cavities
+    if (s->cfg.turb || s->active) return TWO_NONE;
+    // fp32 gains less from the tiles (ALU-bound) and loses on narrow cavities: 8 x 32 cavities of 384^2 ran at
+    // 666 537 MLUPS with them against 690 216 without
+    if (s->esz == 4 && s->cfg.nx < 1024) return TWO_NONE;
+    if (s->fused2_tile < 0 && nodes >= LBM_FUSED2_SMALL_NODES && nodes < LBM_FUSED2_LARGE_NODES) return TWO_NONE;
+    return TWO_TILE;
 }
+static bool fused2_capable(const lbm_solver* s) { return two_step_kind(s) != TWO_NONE; }
 // ... and to lbm_step, which owns whole cavities only
 static bool fused2_usable(const lbm_solver* s) { return fused2_capable(s) && s->nyl == s->cfg.ny; }
+
+// Rows per segment of the marching kernel: as tall as possible (a segment recomputes one row above and below
+// itself) while the launch still has a few work items per resident warp slot.
+// Rows per segment of the sliding-window kernel: 4m - 2 (m iterations of four rows cover the segment and its two
+// halo rows exactly), as tall as possible while the launch keeps several CTAs per resident slot (3 per SM).
+static int slide_seg_h(const lbm_solver* s) {
+    if (s->slide_h > 0) return s->slide_h;
+    const int tx = 512 / s->esz;
+    const long long nsx = (s->cfg.nx + tx - 1) / tx;
+    const long long want = 4LL * s->num_sms * 3;
+    for (int h = 126; h > 14; h = (h + 2) / 2 - 2)
+        if (nsx * ((s->nyl + h - 1) / h) * s->cfg.batch >= want) return h;
+    return 14;
+}
+
+static int march_seg_h(const lbm_solver* s) {
+    if (s->march_h > 0) return s->march_h;
+    const int cols = march2_cols(s->esz, s->march_variant);
+    const long long nsx = (s->cfg.nx + cols - 1) / cols;
+    const long long want = 3LL * s->num_sms * 16;
+    for (int h = 64; h > 8; h >>= 1)
+        if (nsx * ((s->nyl + h - 1) / h) * s->cfg.batch >= want) return h;
+    return 8;
+}
 
 // Tile-shape variant of the two-step kernel.  Defaults from tools/fused2_sweep.py at 4096^2: fp64 64x8 tiles at
 // 4 CTAs/SM, fp32 32x16; cavities small enough to be launch-latency-bound take 32x8 tiles so that one wave still
@@ -403,6 +463,8 @@ static cudaError_t launch_fused2_t(lbm_solver* s, const StepArgs& a, bool macros
 
 // Tile height of the fused kernel in use (needed to cut a strip into edge / interior bands of whole tile rows).
 static int fused2_tile_height(const lbm_solver* s) {
+    if (two_step_kind(s) == TWO_MARCH) return march_seg_h(s);
+    if (two_step_kind(s) == TWO_SLIDE) return slide_seg_h(s);
     switch (fused2_variant(s)) {
         case 1: case 3: case 9: return 8;
         default: return 16;
@@ -417,6 +479,27 @@ static int launch_fused2_rows(lbm_solver* s, int row_begin, int row_count, bool 
     a.row_begin = row_begin; a.row_count = row_count;
     a.ghost2 = (char*)s->f[s->cur] + (size_t)s->cfg.batch * s->cavity * s->esz;
     cudaError_t e;
+    if (two_step_kind(s) == TWO_SLIDE) {
+        a.seg_h = slide_seg_h(s);
+        Slide2Launch L{};
+        L.coll = s->cfg.collision == LBM_SRT ? COLL_SRT : s->cfg.collision == LBM_TRT ? COLL_TRT : COLL_MRT;
+        L.macros = macros; L.batch = s->cfg.batch; L.pdl = s->use_pdl != 0; L.st = st;
+        e = s->esz == 8 ? launch_slide2_f64(a, L) : launch_slide2_f32(a, L);
+        if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("sliding two-step launch: ") + cudaGetErrorString(e));
+        s->launches++;
+        return LBM_OK;
+    }
+    if (two_step_kind(s) == TWO_MARCH) {
+        a.seg_h = march_seg_h(s);
+        March2Launch L{};
+        L.coll = s->cfg.collision == LBM_SRT ? COLL_SRT : s->cfg.collision == LBM_TRT ? COLL_TRT : COLL_MRT;
+        L.turb = s->cfg.turb != 0; L.macros = macros; L.variant = s->march_variant; L.batch = s->cfg.batch;
+        L.pdl = s->use_pdl != 0; L.st = st;
+        e = s->esz == 8 ? launch_march2_f64(a, L) : launch_march2_f32(a, L);
+        if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("marching two-step launch: ") + cudaGetErrorString(e));
+        s->launches++;
+        return LBM_OK;
+    }
     if (s->cfg.dtype == LBM_F64) {
         e = s->cfg.collision == LBM_SRT ? launch_fused2_t<double, COLL_SRT>(s, a, macros, st)
           : s->cfg.collision == LBM_TRT ? launch_fused2_t<double, COLL_TRT>(s, a, macros, st)
@@ -463,7 +546,7 @@ static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin,
     L.st = st;
     L.pdl = s->use_pdl && mode == MODE_STEP;
     block_shape(vec ? (s->cfg.nx + vw - 1) / vw : s->cfg.nx, row_count, s->cfg.batch, &L);
-    if (L.grid.y > 65535u || L.grid.z > 65535u) {
+    if (L.grid.y > 65535u) {
         // split over rows in chunks the grid can express
         const int chunk = 65535;
         for (int off = 0; off < row_count; off += chunk) {
@@ -523,7 +606,7 @@ int lbm_device_count(int* count) {
 static int check_cfg(const lbm_config_t* c, int* nyl_out) {
     if (!c) return fail(LBM_EINVAL, "cfg == NULL");
     if (c->nx < 3 || c->ny < 3) return fail(LBM_EINVAL, "nx and ny must be >= 3");
-    if (c->batch < 1) return fail(LBM_EINVAL, "batch must be >= 1");
+    if (c->batch < 1 || c->batch > 65535) return fail(LBM_EINVAL, "batch must lie in [1, 65535] (grid.z = cavity)");
     if (c->dtype != LBM_F32 && c->dtype != LBM_F64) return fail(LBM_EINVAL, "dtype must be LBM_F32 or LBM_F64");
     if (c->collision < LBM_SRT || c->collision > LBM_MRT) return fail(LBM_EINVAL, "bad collision");
     if (c->turb != 0 && c->turb != 1) return fail(LBM_EINVAL, "turb must be 0 or 1");
@@ -604,19 +687,6 @@ int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
     s->plane = L.plane; s->cavity = L.cavity; s->mplane = (long long)nyl * L.pitch;
     s->state_bytes = (size_t)L.state_bytes;
     s->engine = cfg->engine == LBM_ENGINE_TMA ? LBM_ENGINE_TMA : LBM_ENGINE_LDG;   // AUTO -> ldg
-    if (const char* ev = getenv("LBM_B200_ENGINE")) {         // development override
-        if (!strcmp(ev, "tma")) s->engine = LBM_ENGINE_TMA;
-        if (!strcmp(ev, "ldg")) s->engine = LBM_ENGINE_LDG;
-    }
-    if (const char* ev = getenv("LBM_B200_VEC_F64")) s->vec_f64 = atoi(ev) == 2 ? 2 : 1;
-    if (const char* ev = getenv("LBM_B200_VEC_F32")) s->vec_f32 = (atoi(ev) == 2 || atoi(ev) == 4) ? atoi(ev) : 1;
-    if (const char* ev = getenv("LBM_B200_GRAPH")) s->use_graph = atoi(ev) != 0;
-    if (const char* ev = getenv("LBM_B200_PDL")) s->use_pdl = atoi(ev) != 0;
-    if (const char* ev = getenv("LBM_B200_FUSED2")) s->use_fused2 = atoi(ev) != 0;
-    if (const char* ev = getenv("LBM_B200_FUSED2_TILE")) s->fused2_tile = atoi(ev);
-    if (const char* ev = getenv("LBM_B200_FUSED2_MIN_NODES")) s->fused2_min_nodes = atoll(ev);
-    if (const char* ev = getenv("LBM_B200_TMA_VARIANT")) s->tma_variant = atoi(ev) % LBM_TMA_VARIANTS;
-    if (const char* ev = getenv("LBM_B200_TMA_CTAS")) s->tma_ctas_per_sm = atoi(ev) > 0 ? atoi(ev) : 1;
 #define CKD(call)                                                                       \
     do {                                                                                \
         cudaError_t e__ = (call);                                                       \
@@ -648,11 +718,11 @@ int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
     CKD(cudaMalloc(&s->carry, 2 * (size_t)cfg->batch * 4 * s->esz));
     CKD(cudaMemset(s->carry, 0, 2 * (size_t)cfg->batch * 4 * s->esz));
     CKD(cudaMalloc(&s->cav, sizeof(CavityParams) * cfg->batch));
-    if (cfg->turb) {
-        CKD(cudaMalloc(&s->pi_eq, mbytes));
-        CKD(cudaMalloc(&s->rho_prev, mbytes));
-        CKD(cudaMemset(s->pi_eq, 0, mbytes));
-        CKD(cudaMemset(s->rho_prev, 0, mbytes));
+    if (cfg->turb) {       // two halves each: the two-step kernel reads one and writes the other (see `side`)
+        CKD(cudaMalloc(&s->pi_eq, 2 * mbytes));
+        CKD(cudaMalloc(&s->rho_prev, 2 * mbytes));
+        CKD(cudaMemset(s->pi_eq, 0, 2 * mbytes));
+        CKD(cudaMemset(s->rho_prev, 0, 2 * mbytes));
     }
 #undef CKD
     s->cav_host.resize(cfg->batch);
@@ -674,6 +744,43 @@ int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
 int lbm_get_layout(lbm_handle_t s, lbm_layout_t* out) {
     if (!s || !out) return fail(LBM_EINVAL, "NULL argument");
     layout_of(&s->cfg, s->nyl, out);
+    return LBM_OK;
+}
+
+static void drop_graphs(lbm_solver* s) {
+    for (int i = 0; i < 4; ++i)
+        if (s->graph[i]) { cudaGraphExecDestroy(s->graph[i]); s->graph[i] = nullptr; }
+}
+
+int lbm_set_tuning(lbm_handle_t s, const char* key, int64_t value) {
+    if (!s || !key) return fail(LBM_EINVAL, "NULL argument");
+    const std::string k(key);
+    const int v = (int)value;
+    if (k == "two_step") s->use_fused2 = v != 0;
+    else if (k == "march") s->use_march = v != 0;
+    else if (k == "march_variant") {
+        if (v < 0 || march2_cols(s->esz, v) == 0) return fail(LBM_EINVAL, "march_variant out of range");
+        s->march_variant = v;
+    }
+    else if (k == "march_h") { if (v < 0 || v > 4096) return fail(LBM_EINVAL, "march_h must lie in [0, 4096]"); s->march_h = v; }
+    else if (k == "march_min_nodes") s->march_min_nodes = value;
+    else if (k == "slide") s->use_slide = v != 0;
+    else if (k == "slide_h") { if (v < 0 || v > 4096) return fail(LBM_EINVAL, "slide_h must lie in [0, 4096]"); s->slide_h = v; }
+    else if (k == "slide_min_nodes") s->slide_min_nodes = value;
+    else if (k == "tile") { if (v < -1 || v > 9) return fail(LBM_EINVAL, "tile must lie in [-1, 9]"); s->fused2_tile = v; }
+    else if (k == "two_step_min_nodes") s->fused2_min_nodes = value;
+    else if (k == "vec_f64") { if (v != 1 && v != 2) return fail(LBM_EINVAL, "vec_f64 must be 1 or 2"); s->vec_f64 = v; }
+    else if (k == "vec_f32") { if (v != 1 && v != 2 && v != 4) return fail(LBM_EINVAL, "vec_f32 must be 1, 2 or 4"); s->vec_f32 = v; }
+    else if (k == "graph") s->use_graph = v != 0;
+    else if (k == "pdl") s->use_pdl = v != 0;
+    else if (k == "tma_ctas") { if (v < 1) return fail(LBM_EINVAL, "tma_ctas must be >= 1"); s->tma_ctas_per_sm = v; }
+    else if (k == "tma_variant") {
+        if (v < 0 || v >= LBM_TMA_VARIANTS) return fail(LBM_EINVAL, "tma_variant out of range");
+        s->tma_variant = v;
+        if (s->engine == LBM_ENGINE_TMA) { int rc = make_tensor_maps(s); if (rc) return rc; }
+    }
+    else return fail(LBM_EINVAL, "unknown tuning key '" + k + "'");
+    drop_graphs(s);          // captured launch sequences depend on every one of these
     return LBM_OK;
 }
 
@@ -822,8 +929,13 @@ int lbm_download_f(lbm_handle_t s, void* f, int on_device, void* stream) {
     if (rc) return rc;
     void* fin = s->f[s->cur];
     if (!s->pre) {
-        // gather + wall rule (no collision) into the buffer the next step will overwrite anyway
+        // gather + wall rule (no collision) into the buffer the next step will overwrite anyway -- except with frozen
+        // cavities, whose two buffers must both keep the post-collision state (no step rewrites them): scratch then
         void* dst = s->f[s->cur ^ 1];
+        if (s->active) {
+            if (!s->scratch) CK(cudaMalloc(&s->scratch, s->state_bytes));
+            dst = s->scratch;
+        }
         rc = launch_pass(s, s->f[s->cur], dst, 0, s->nyl, 1, true, false, MODE_FINALIZE, st);
         if (rc) return rc;
         fin = dst;
@@ -1151,25 +1263,40 @@ int lbm_mean_u(lbm_handle_t s, double* mean_out, void* stream) {
 
 int lbm_set_active(lbm_handle_t s, const int32_t* active, void* stream) {
     if (!s || !active) return fail(LBM_EINVAL, "NULL argument");
+    if (s->pre) return fail(LBM_ESTATE, "cavities can be frozen only after at least one step (post-collision state)");
     int rc = set_device(s);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = s->cfg.batch;
+    for (int b = 0; b < nb; ++b)       // validate everything before touching any state
+        if (s->active && !s->active_host[b] && active[b]) return fail(LBM_ESTATE, "a frozen cavity cannot be re-activated");
     if (!s->active) {
         CK(cudaMalloc(&s->active, sizeof(int) * nb));
         s->active_host.assign(nb, 1);
-        for (int i = 0; i < 4; ++i)
-            if (s->graph[i]) { cudaGraphExecDestroy(s->graph[i]); s->graph[i] = nullptr; }   // kernel args change
+        drop_graphs(s);                // kernel args change
     }
     const size_t cav_bytes = (size_t)s->cavity * s->esz;
+    const size_t rl_bytes = (size_t)s->pitch * s->esz, rl_half = (size_t)nb * rl_bytes;
+    const size_t ca_bytes = 4 * (size_t)s->esz, ca_half = (size_t)nb * ca_bytes;
+    const size_t m_bytes = (size_t)s->mplane * s->esz, m_half = (size_t)nb * m_bytes;
+    const int o = s->side ^ 1;
     for (int b = 0; b < nb; ++b) {
         const int now = active[b] ? 1 : 0;
         if (s->active_host[b] && !now) {
-            // freeze: both A/B buffers must hold the cavity's current populations, whatever the parity later on
+            // freeze: both A/B buffers and both halves of the side arrays must hold the cavity's current state,
+            // whatever the parities later on
             CK(cudaMemcpyAsync((char*)s->f[s->cur ^ 1] + b * cav_bytes, (char*)s->f[s->cur] + b * cav_bytes, cav_bytes,
                                cudaMemcpyDeviceToDevice, st));
-        } else if (!s->active_host[b] && now) {
-            return fail(LBM_ESTATE, "a frozen cavity cannot be re-activated");
+            CK(cudaMemcpyAsync((char*)s->rho_lid + o * rl_half + b * rl_bytes, (char*)s->rho_lid + s->side * rl_half + b * rl_bytes,
+                               rl_bytes, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync((char*)s->carry + o * ca_half + b * ca_bytes, (char*)s->carry + s->side * ca_half + b * ca_bytes,
+                               ca_bytes, cudaMemcpyDeviceToDevice, st));
+            if (s->pi_eq) {
+                CK(cudaMemcpyAsync((char*)s->pi_eq + o * m_half + b * m_bytes, (char*)s->pi_eq + s->side * m_half + b * m_bytes,
+                                   m_bytes, cudaMemcpyDeviceToDevice, st));
+                CK(cudaMemcpyAsync((char*)s->rho_prev + o * m_half + b * m_bytes,
+                                   (char*)s->rho_prev + s->side * m_half + b * m_bytes, m_bytes, cudaMemcpyDeviceToDevice, st));
+            }
         }
         s->active_host[b] = now;
     }

@@ -40,6 +40,8 @@ struct StepArgs {
     const void* ghost2;        // fused kernel on a y-strip: [batch][top|bottom][3][pitch] second ghost rows of `src`
     void* pi_eq;               // [batch][nyl][pitch]  sum_k cx cy feq_k of the previous step (Smagorinsky only)
     void* rho_prev;            // [batch][nyl][pitch]  rho of the previous step            (Smagorinsky only)
+    void* pi_eq_out;           // two-step kernels: the other half of the double-buffered Smagorinsky state (one-step
+    void* rho_prev_out;        //   kernels update in place)
     const CavityParams* cav;   // [batch]
     const int* active;         // [batch] or NULL: cavities with active[b] == 0 are frozen (skipped by step launches)
     int nx, ny, y0, nyl, pitch;
@@ -47,6 +49,7 @@ struct StepArgs {
     long long mplane;          // macro plane = nyl * pitch elements
     int row_begin, row_stride; // local row of launch row 0 and distance between consecutive launch rows
     int row_count;             // launch rows (blockIdx.y * blockDim.y + threadIdx.y < row_count)
+    int seg_h, nsx;            // marching two-step kernel: rows per segment, number of x-strips (one warp each)
 };
 
 template <typename T>
@@ -62,24 +65,47 @@ template <typename T> __device__ __forceinline__ T w_rest() { return (T)(4.0 / 9
 template <typename T> __device__ __forceinline__ T w_axis() { return (T)(1.0 / 9.0); }
 template <typename T> __device__ __forceinline__ T w_diag() { return (T)(1.0 / 36.0); }
 
-// feq_k = rho*t_k*(1. + 3.0*cu + 9*0.5*cu*cu - 3.0*0.5*usqr), operation order of MRT_GPU.py:651.
+// ---- rounding discipline ----------------------------------------------------------------------------------------
+// The library is compiled with -fmad=false: the compiler never contracts a*b+c on its own, every fused multiply-add
+// below is spelled fm(a, b, c).  What a node computes is therefore fixed by this file alone and does not depend on
+// which kernel inlines it -- the one-step, shared-memory-tile and marching kernels are bit-identical by construction
+// (with implicit contraction the fp64 SRT / TRT paths of two kernel families were seen to differ in the last bit).
+__device__ __forceinline__ float fm(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fm(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// feq_k = rho*t_k*(1. + 3.0*cu + 9*0.5*cu*cu - 3.0*0.5*usqr)   (MRT_GPU.py:651), Horner in cu; rt = rho * t_k.
 template <typename T>
-__device__ __forceinline__ T feq_one(T rho, T tk, T cu, T usqr) {
-    return rho * tk * ((T)1.0 + (T)3.0 * cu + (T)4.5 * cu * cu - (T)1.5 * usqr);
+__device__ __forceinline__ T feq_one(T rt, T cu, T usqr) {
+    return rt * fm((T)-1.5, usqr, fm(cu, fm((T)4.5, cu, (T)3.0), (T)1.0));
 }
 
 template <typename T>
 __device__ __forceinline__ void feq_all(T rho, T ux, T uy, T fe[9]) {
+    const T usqr = fm(ux, ux, uy * uy);
+    const T r0 = rho * w_rest<T>(), r1 = rho * w_axis<T>(), r2 = rho * w_diag<T>();
+    fe[0] = r0 * fm((T)-1.5, usqr, (T)1.0);
+    fe[1] = feq_one(r1, ux, usqr);
+    fe[2] = feq_one(r1, uy, usqr);
+    fe[3] = feq_one(r1, -ux, usqr);
+    fe[4] = feq_one(r1, -uy, usqr);
+    fe[5] = feq_one(r2, ux + uy, usqr);
+    fe[6] = feq_one(r2, uy - ux, usqr);
+    fe[7] = feq_one(r2, -(ux + uy), usqr);
+    fe[8] = feq_one(r2, ux - uy, usqr);
+}
+
+// The same equilibrium in the reference's own operation order and without any fused operation (MRT.py:213-231,
+// functions.pyx:229-267): bit-identical to the NumPy / Cython expression.  Used off the hot path, where the result is
+// handed to the caller as data: the initial state (lbm_init_eq) and functions.equ (lbm_equ_kernel).
+template <typename T>
+__device__ __forceinline__ void feq_all_ref(T rho, T ux, T uy, T fe[9]) {
     const T usqr = ux * ux + uy * uy;
-    fe[0] = feq_one(rho, w_rest<T>(), (T)0, usqr);
-    fe[1] = feq_one(rho, w_axis<T>(), ux, usqr);
-    fe[2] = feq_one(rho, w_axis<T>(), uy, usqr);
-    fe[3] = feq_one(rho, w_axis<T>(), -ux, usqr);
-    fe[4] = feq_one(rho, w_axis<T>(), -uy, usqr);
-    fe[5] = feq_one(rho, w_diag<T>(), ux + uy, usqr);
-    fe[6] = feq_one(rho, w_diag<T>(), -ux + uy, usqr);
-    fe[7] = feq_one(rho, w_diag<T>(), -ux - uy, usqr);
-    fe[8] = feq_one(rho, w_diag<T>(), ux - uy, usqr);
+    const T cu[9] = {(T)0, ux, uy, -ux, -uy, ux + uy, -ux + uy, -ux - uy, ux - uy};
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const T tk = k == 0 ? w_rest<T>() : (k < 5 ? w_axis<T>() : w_diag<T>());
+        fe[k] = rho * tk * ((T)1.0 + (T)3.0 * cu[k] + (T)4.5 * cu[k] * cu[k] - (T)1.5 * usqr);
+    }
 }
 
 // Wall rule on the post-stream populations f of a wall node (funBC, MRT_GPU.py:674-692): x-block, then y-block,
@@ -144,7 +170,7 @@ __device__ __forceinline__ void moments_ref(const T f[9], T& rho, T& jx, T& jy) 
 // Lid density, MRT_GPU.py:627.
 template <typename T>
 __device__ __forceinline__ T rho_lid_formula(const T f[9]) {
-    return f[0] + f[1] + f[3] + (T)2 * (f[2] + f[5] + f[6]);
+    return fm((T)2, f[2] + f[5] + f[6], f[0] + f[1] + f[3]);
 }
 
 // ---- collisions ---------------------------------------------------------------------------------------------
@@ -154,24 +180,24 @@ __device__ __forceinline__ void collide_srt(T f[9], T rho, T ux, T uy, T omega) 
     T fe[9];
     feq_all<T>(rho, ux, uy, fe);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) f[k] = f[k] - omega * (f[k] - fe[k]);
+    for (int k = 0; k < 9; ++k) f[k] = fm(-omega, f[k] - fe[k], f[k]);
 }
 
-// TRT: f - omega+ (f+ - feq+) - omega- (f- - feq-)   (MRT_GPU.py:455-462, 514-527)
+// TRT: f - omega+ (f+ - feq+) - omega- (f- - feq-)   (MRT_GPU.py:455-462, 514-527); the halves are folded into the rates
 template <typename T>
 __device__ __forceinline__ void collide_trt(T f[9], T rho, T ux, T uy, T omegap, T omegam) {
     T fe[9];
     feq_all<T>(rho, ux, uy, fe);
-    const T h = (T)0.5;
-    f[0] = f[0] - omegap * (f[0] - fe[0]) - omegam * ((T)0 - (T)0);
+    const T hp = (T)0.5 * omegap, hm = (T)0.5 * omegam;
+    f[0] = fm(-omegap, f[0] - fe[0], f[0]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int a = (i < 2) ? i + 1 : i + 3;     // a = 1, 2, 5, 6
         const int o = a + 2;                       // 1<->3, 2<->4, 5<->7, 6<->8
-        const T fp = h * (f[a] + f[o]), fm = h * (f[a] - f[o]);
-        const T ep = h * (fe[a] + fe[o]), em = h * (fe[a] - fe[o]);
-        const T fa = f[a] - omegap * (fp - ep) - omegam * (fm - em);
-        const T fo = f[o] - omegap * (fp - ep) - omegam * (-fm - (-em));
+        const T sp = (f[a] + f[o]) - (fe[a] + fe[o]);     // 2 (f+ - feq+)
+        const T sm = (f[a] - f[o]) - (fe[a] - fe[o]);     // 2 (f- - feq-)   (opposite sign for o)
+        const T fa = fm(-hm, sm, fm(-hp, sp, f[a]));
+        const T fo = fm(hm, sm, fm(-hp, sp, f[o]));
         f[a] = fa;
         f[o] = fo;
     }
@@ -182,58 +208,60 @@ __device__ __forceinline__ void collide_trt(T f[9], T rho, T ux, T uy, T omegap,
 // conserved density (measured: 3e-6 in rho, 1e-5 of uLB in u after 150 steps at tau = 0.54, ten times the MRT path,
 // whose correction form never rounds at the magnitude of f).  The same collision evaluated on the deviations
 // g_k = f_k - t_k (exact by Sterbenz) and feq_k - t_k = t_k (drho + rho (3cu + 4.5cu^2 - 1.5u^2)) only rounds at the
-// magnitude of the deviations.  Used for T = float only; fp64 keeps the reference's operation order.
+// magnitude of the deviations.  Used for T = float only; fp64 evaluates the populations themselves.
 // (The reference's own fp32 kernels evaluate these expressions with double literals, i.e. in mixed precision.)
 template <typename T>
 __device__ __forceinline__ T drho_of(const T f[9], bool lid) {
     const T g0 = f[0] - w_rest<T>(), g1 = f[1] - w_axis<T>(), g2 = f[2] - w_axis<T>(), g3 = f[3] - w_axis<T>(),
             g4 = f[4] - w_axis<T>(), g5 = f[5] - w_diag<T>(), g6 = f[6] - w_diag<T>(), g7 = f[7] - w_diag<T>(),
             g8 = f[8] - w_diag<T>();
-    if (lid) return g0 + g1 + g3 + (T)2 * (g2 + g5 + g6);        // lid formula: the weights sum to exactly 1
+    if (lid) return fm((T)2, g2 + g5 + g6, g0 + g1 + g3);        // lid formula: the weights sum to exactly 1
     return g0 + g1 + g2 + g3 + g4 + g5 + g6 + g7 + g8;
 }
 template <typename T>
+__device__ __forceinline__ T weight_of(int k) { return k == 0 ? w_rest<T>() : (k < 5 ? w_axis<T>() : w_diag<T>()); }
+template <typename T>
 __device__ __forceinline__ void feq_dev_all(T drho, T rho, T ux, T uy, T fd[9]) {
-    const T usqr = ux * ux + uy * uy;
-    const T cu[9] = {(T)0, ux, uy, -ux, -uy, ux + uy, -ux + uy, -ux - uy, ux - uy};
+    const T usqr = fm(ux, ux, uy * uy);
+    const T cu[9] = {(T)0, ux, uy, -ux, -uy, ux + uy, uy - ux, -(ux + uy), ux - uy};
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-        const T tk = k == 0 ? w_rest<T>() : (k < 5 ? w_axis<T>() : w_diag<T>());
-        fd[k] = tk * (drho + rho * ((T)3.0 * cu[k] + (T)4.5 * cu[k] * cu[k] - (T)1.5 * usqr));
+        const T q = fm((T)-1.5, usqr, cu[k] * fm((T)4.5, cu[k], (T)3.0));     // 3cu + 4.5cu^2 - 1.5u^2
+        fd[k] = weight_of<T>(k) * fm(rho, q, drho);
     }
 }
-template <typename T>
-__device__ __forceinline__ T weight_of(int k) { return k == 0 ? w_rest<T>() : (k < 5 ? w_axis<T>() : w_diag<T>()); }
 
 template <typename T>
 __device__ __forceinline__ void collide_srt_dev(T f[9], T drho, T rho, T ux, T uy, T omega) {
     T fd[9];
     feq_dev_all<T>(drho, rho, ux, uy, fd);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) f[k] = f[k] - omega * ((f[k] - weight_of<T>(k)) - fd[k]);
+    for (int k = 0; k < 9; ++k) f[k] = fm(-omega, (f[k] - weight_of<T>(k)) - fd[k], f[k]);
 }
 template <typename T>
 __device__ __forceinline__ void collide_trt_dev(T f[9], T drho, T rho, T ux, T uy, T omegap, T omegam) {
     T fd[9];
     feq_dev_all<T>(drho, rho, ux, uy, fd);
-    const T h = (T)0.5;
-    f[0] = f[0] - omegap * ((f[0] - w_rest<T>()) - fd[0]);
+    const T hp = (T)0.5 * omegap, hm = (T)0.5 * omegam;
+    f[0] = fm(-omegap, (f[0] - w_rest<T>()) - fd[0], f[0]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int a = (i < 2) ? i + 1 : i + 3;
         const int o = a + 2;
         const T ga = f[a] - weight_of<T>(a), go = f[o] - weight_of<T>(o);
-        const T sp = h * ((ga + go) - (fd[a] + fd[o]));      // f+ - feq+
-        const T sm = h * ((ga - go) - (fd[a] - fd[o]));      // f- - feq-   (opposite sign for o)
-        f[a] = f[a] - omegap * sp - omegam * sm;
-        f[o] = f[o] - omegap * sp + omegam * sm;
+        const T sp = (ga + go) - (fd[a] + fd[o]);      // 2 (f+ - feq+)
+        const T sm = (ga - go) - (fd[a] - fd[o]);      // 2 (f- - feq-)   (opposite sign for o)
+        const T fa = fm(-hm, sm, fm(-hp, sp, f[a]));
+        const T fo = fm(hm, sm, fm(-hp, sp, f[o]));
+        f[a] = fa;
+        f[o] = fo;
     }
 }
 
 // MRT in the Gram-Schmidt basis of MRT_GPU.py:593-612 with the reference's (non-standard) equilibrium moments
 // (:636-644: momentum not velocity, +9 jx^2 jy^2, cubic heat-flux terms) and rates s = [0,s_e,s_eps,0,s_q,0,s_q,s_nu,s_nu].
 // Evaluated as f* = f - Minv * S * (m - m_eq) with M and Minv hand-factored (entries 0,+-1,+-2,+-4 / 1/4..1/36):
-// ~80 flops instead of two dense 9x9 products.  Rounding differs from the reference's "Minv * m*" form at the
+// ~80 operations instead of two dense 9x9 products.  Rounding differs from the reference's "Minv * m*" form at the
 // 1e-16 level per step (measured 5e-14 in rho after 1000 steps at 96^2, Re 3200; tolerance 1e-12).
 template <typename T>
 __device__ __forceinline__ void collide_mrt(T f[9], T rho, T s_e, T s_eps, T s_q, T s_nu) {
@@ -246,34 +274,32 @@ __device__ __forceinline__ void collide_mrt(T f[9], T rho, T s_e, T s_eps, T s_q
     const T pxy = s57 - s68;
     const T ab = p13 + p24;
     const T jx = m13 + jxd, jy = m24 + jyd;
-    const T e = (T)2 * dg - ab - (T)4 * f[0];
-    const T eps = (T)4 * f[0] - (T)2 * ab + dg;
-    const T qx = jxd - (T)2 * m13, qy = jyd - (T)2 * m24;
+    const T e = fm((T)-4, f[0], fm((T)2, dg, -ab));
+    const T eps = fm((T)4, f[0], fm((T)-2, ab, dg));
+    const T qx = fm((T)-2, m13, jxd), qy = fm((T)-2, m24, jyd);
     const T pxx = p13 - p24;
     const T jx2 = jx * jx, jy2 = jy * jy, sq = jx2 + jy2;
-    const T e_eq = (T)3 * sq - (T)2 * rho;
-    const T eps_eq = rho - (T)3 * sq + (T)9 * (jx2 * jy2);
-    const T qx_eq = jx * ((T)3 * jx2 - (T)1);
-    const T qy_eq = jy * ((T)3 * jy2 - (T)1);
+    const T e_eq = fm((T)3, sq, (T)-2 * rho);
+    const T eps_eq = fm((T)9, jx2 * jy2, fm((T)-3, sq, rho));
+    const T qx_eq = jx * fm((T)3, jx2, (T)-1);
+    const T qy_eq = jy * fm((T)3, jy2, (T)-1);
     const T pxx_eq = jx2 - jy2, pxy_eq = jx * jy;
     const T de = s_e * (e - e_eq);
     const T dp = s_eps * (eps - eps_eq);
     const T dqx = s_q * (qx - qx_eq), dqy = s_q * (qy - qy_eq);
     const T dxx = s_nu * (pxx - pxx_eq), dxy = s_nu * (pxy - pxy_eq);
     const T c0 = (de - dp) * (T)(1.0 / 9.0);
-    const T cax = (de + (T)2 * dp) * (T)(1.0 / 36.0);
-    const T cdg = -((T)2 * de + dp) * (T)(1.0 / 36.0);
-    const T qx6 = dqx * (T)(1.0 / 6.0), qy6 = dqy * (T)(1.0 / 6.0);
-    const T qx12 = dqx * (T)(1.0 / 12.0), qy12 = dqy * (T)(1.0 / 12.0);
-    const T xx4 = dxx * (T)0.25, xy4 = dxy * (T)0.25;
-    const T ax_m = cax - xx4, ax_p = cax + xx4;
-    const T dg_m = cdg - xy4, dg_p = cdg + xy4;
-    const T qs = qx12 + qy12, qd = qx12 - qy12;
+    const T cax = fm((T)2, dp, de) * (T)(1.0 / 36.0);
+    const T cdg = fm((T)2, de, dp) * (T)(-1.0 / 36.0);
+    const T ax_m = fm((T)-0.25, dxx, cax), ax_p = fm((T)0.25, dxx, cax);
+    const T dg_m = fm((T)-0.25, dxy, cdg), dg_p = fm((T)0.25, dxy, cdg);
+    const T qs = (dqx + dqy) * (T)(1.0 / 12.0), qd = (dqx - dqy) * (T)(1.0 / 12.0);
+    const T s6 = (T)(1.0 / 6.0);
     f[0] = f[0] + c0;
-    f[1] = f[1] + (ax_m + qx6);
-    f[3] = f[3] + (ax_m - qx6);
-    f[2] = f[2] + (ax_p + qy6);
-    f[4] = f[4] + (ax_p - qy6);
+    f[1] = f[1] + fm(s6, dqx, ax_m);
+    f[3] = f[3] + fm(-s6, dqx, ax_m);
+    f[2] = f[2] + fm(s6, dqy, ax_p);
+    f[4] = f[4] + fm(-s6, dqy, ax_p);
     f[5] = f[5] + (dg_m - qs);
     f[6] = f[6] + (dg_p + qd);
     f[7] = f[7] + (dg_m + qs);
@@ -287,7 +313,7 @@ template <typename T>
 __device__ __forceinline__ T smagorinsky_omega(const T f[9], T pi_prev, T rho_prev, T tau0) {
     const T product1 = f[5] - f[6] + f[7] - f[8];
     const T Qmf = product1 - pi_prev;
-    const T tau = (T)0.5 * (tau0 + sqrt(tau0 * tau0 + ((T)(18 * 1.4142 * 0.025) * fabs(Qmf)) / rho_prev));
+    const T tau = (T)0.5 * (tau0 + sqrt(fm(tau0, tau0, ((T)(18 * 1.4142 * 0.025) * fabs(Qmf)) / rho_prev)));
     return (T)1.0 / tau;
 }
 
@@ -299,15 +325,10 @@ __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left
     T rho, jx, jy;
     moments_ref<T>(f, rho, jx, jy);
     T ux = (T)0, uy = (T)0;
-    if (NEED_U || TURB || COLL != COLL_MRT) {
-        if (sizeof(T) == 4 || (TURB && COLL == COLL_MRT)) {   // one reciprocal + two multiplies (fp64 SRT/TRT keep true divisions)
-            const T inv = (T)1 / rho;
-            ux = jx * inv;
-            uy = jy * inv;
-        } else {
-            ux = jx / rho;
-            uy = jy / rho;
-        }
+    if (NEED_U || TURB || COLL != COLL_MRT) {      // u = j / rho as one reciprocal and two multiplications
+        const T inv = (T)1 / rho;
+        ux = jx * inv;
+        uy = jy * inv;
     }
     if (left || right || bot) { ux = (T)0; uy = (T)0; }
     if (lid) {
@@ -317,10 +338,11 @@ __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left
     }
     rho_out = rho; ux_out = ux; uy_out = uy;
     const T om = TURB ? omega_nu : r.omega;
-    if (TURB) {
-        const T usqr = ux * ux + uy * uy;
-        const T fe5 = feq_one(rho, w_diag<T>(), ux + uy, usqr), fe6 = feq_one(rho, w_diag<T>(), -ux + uy, usqr);
-        const T fe7 = feq_one(rho, w_diag<T>(), -ux - uy, usqr), fe8 = feq_one(rho, w_diag<T>(), ux - uy, usqr);
+    if (TURB) {       // sum_k cx cy feq_k = feq5 - feq6 + feq7 - feq8, the next step's pi_prev
+        const T usqr = fm(ux, ux, uy * uy);
+        const T r2 = rho * w_diag<T>();
+        const T fe5 = feq_one(r2, ux + uy, usqr), fe6 = feq_one(r2, uy - ux, usqr);
+        const T fe7 = feq_one(r2, -(ux + uy), usqr), fe8 = feq_one(r2, ux - uy, usqr);
         *pi_out = fe5 - fe6 + fe7 - fe8;
     }
     if (COLL == COLL_MRT) {

@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(256) lbm_step_ldg(const StepArgs a) {
         // current-state moments with the reference's overrides, no collision
         T jx, jy;
         moments_ref<T>(f, rho, jx, jy);
-        ux = jx / rho; uy = jy / rho;
+        const T inv = (T)1 / rho;                                  // same form as node_update
+        ux = jx * inv; uy = jy * inv;
         if (left || right || bot) { ux = (T)0; uy = (T)0; }
         if (lid) { rho = rho_lid_formula<T>(f); ux = r.uLB; uy = (T)0; }
     } else {
@@ -314,7 +315,12 @@ __global__ void lbm_A_collide(const StepArgs a) {
     if (y == 0) rho = rho_lid_formula<T>(f);                              // MRT.py:337
     if (x == 0 || x == a.nx - 1 || y == a.ny - 1) { ux = (T)0; uy = (T)0; }   // :341
     if (y == 0) { ux = r.uLB; uy = (T)0; }                                // :342
-    collide_srt<T>(f, rho, ux, uy, r.omega);                              // :396
+    {                                                                     // :396, the script's operation order
+        T fe[9];
+        feq_all_ref<T>(rho, ux, uy, fe);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) f[k] = f[k] - r.omega * (f[k] - fe[k]);
+    }
 #pragma unroll
     for (int k = 0; k < 9; ++k) fpost[k * a.plane + rc] = f[k];
     const long long m = (long long)b * a.mplane + (long long)y * a.pitch + x;
@@ -351,7 +357,7 @@ __global__ void lbm_A_stream_bc(const StepArgs a) {
     if (x == 0 || x == nx - 1 || y == 0 || y == ny - 1) {
         const long long m = (long long)b * a.mplane + (long long)y * a.pitch + x;
         T fe[9];
-        feq_all<T>(static_cast<const T*>(a.rho)[m], static_cast<const T*>(a.ux)[m], static_cast<const T*>(a.uy)[m], fe);
+        feq_all_ref<T>(static_cast<const T*>(a.rho)[m], static_cast<const T*>(a.ux)[m], static_cast<const T*>(a.uy)[m], fe);
         if (x == 0) { f[1] = fe[1]; f[5] = fe[5]; f[8] = fe[8]; }                         // :450
         if (x == nx - 1) {                                                                // :451  (3,6,7) <- (1,5,8)
             f[3] = -fe[1] + (fe[3] + f[1]);
@@ -383,7 +389,7 @@ __global__ void lbm_init_eq(StepArgs a) {
     const int y = a.y0 + yl;
     const double ux = (y == 0) ? a.cav[b].uLB : 0.0;
     double fe[9];
-    feq_all<double>(1.0, ux, 0.0, fe);
+    feq_all_ref<double>(1.0, ux, 0.0, fe);
     T* dst = static_cast<T*>(a.dst) + (long long)b * a.cavity;
     const long long rc = (long long)(yl + 1) * a.pitch + x;
 #pragma unroll
@@ -477,7 +483,7 @@ __global__ void lbm_equ_kernel(const T* __restrict__ rho, const T* __restrict__ 
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         T fe[9];
-        feq_all<T>(rho[i], ux[i], uy[i], fe);
+        feq_all_ref<T>(rho[i], ux[i], uy[i], fe);
 #pragma unroll
         for (int k = 0; k < 9; ++k) feq[k * n + i] = fe[k];
     }

@@ -24,6 +24,16 @@ def _dtype_name(dtype) -> str:
     return name
 
 
+def _env_tuning() -> dict:
+    import os
+    out = {}
+    for item in os.environ.get("LBM_B200_TUNING", "").split(","):
+        if item.strip():
+            k, _, v = item.partition("=")
+            out[k.strip()] = int(v)
+    return out
+
+
 def _is_torch_cuda(x) -> bool:
     return type(x).__module__.startswith("torch") and getattr(x, "is_cuda", False)
 
@@ -31,7 +41,8 @@ def _is_torch_cuda(x) -> bool:
 class CavitySolver:
     def __init__(self, nx: int, ny: int, batch: int = 1, dtype="float64", collision: str = "MRT",
                  turb: bool = False, y0: int = 0, ny_local: Optional[int] = None, device: Optional[int] = None,
-                 engine: str = "auto", ext_buffers: Optional[Sequence[int]] = None, semantics: str = "C"):
+                 engine: str = "auto", ext_buffers: Optional[Sequence[int]] = None, semantics: str = "C",
+                 tuning: Optional[dict] = None):
         self._lib = _capi.load()
         self._h = C.c_void_p()
         self.nx, self.ny, self.batch = int(nx), int(ny), int(batch)
@@ -59,6 +70,9 @@ class CavitySolver:
         lay = _capi.Layout()
         _capi.check(self._lib.lbm_get_layout(self._h, C.byref(lay)))
         self.layout = lay
+        # kernel-selection knobs (lbm_set_tuning): LBM_B200_TUNING="key=value,..." for the tools, then the argument
+        for key, value in list(_env_tuning().items()) + list((tuning or {}).items()):
+            self.set_tuning(key, value)
 
     # -- lifetime ---------------------------------------------------------------------------------------------
     def close(self) -> None:
@@ -87,6 +101,10 @@ class CavitySolver:
         out = C.c_size_t()
         _capi.check(lib.lbm_state_bytes(C.byref(cfg), C.byref(out)))
         return int(out.value)
+
+    def set_tuning(self, key: str, value: int) -> None:
+        """Kernel-selection knob (``lbm_set_tuning`` in include/lbm_b200.h); never changes a result."""
+        _capi.check(self._lib.lbm_set_tuning(self._h, str(key).encode(), int(value)))
 
     # -- parameters -------------------------------------------------------------------------------------------
     def set_reynolds(self, Re, uLB: float = 0.08, cavity: int = -1) -> None:
@@ -179,6 +197,8 @@ class CavitySolver:
             u_out = np.empty(us, dtype=self.np_dtype)
         rp, d1, k1 = self._host_arg(rho_out, rs)
         up, d2, k2 = self._host_arg(u_out, us)
+        if (k1 is not rho_out and not d1) or (k2 is not u_out and not d2):
+            raise ValueError("rho_out and u_out must be C-contiguous arrays of the solver's dtype")
         if d1 != d2:
             raise ValueError("rho_out and u_out must both be host or both be device arrays")
         fn = self._lib.lbm_get_macros_current if current else self._lib.lbm_get_macros

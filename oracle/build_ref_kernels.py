@@ -13,6 +13,9 @@ splicing literals in with `%`; PyCUDA is not installed and the values differ per
   * the three variants, all called `funRT`, are renamed funRT_SRT / funRT_TRT / funRT_MRT;
   * a small host driver (ours, below) replaces the Python time loop MRT_GPU.py:707-732: launches funRT then funBC
     with block (32,32,1), grid (nx/32, ny/32), exactly like :724,732.
+A second build, oracle/_ref/libref_kernels_f64.so, is the SAME text with every `float` token replaced by `double`
+(kernel signatures, locals, tables, the parameter array and the driver's buffers): the reference's algorithm in the
+precision the oracle works in, so that the MRT relaxation and funBC are pinned to round-off of fp64, not of fp32.
 """
 from __future__ import annotations
 
@@ -23,6 +26,7 @@ import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref", "libref_kernels.so")
+OUT_F64 = os.path.join(HERE, "_ref", "libref_kernels_f64.so")
 REF_DIR = os.environ.get("LBM_REFERENCE_DIR", "/root/reference")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
@@ -60,7 +64,7 @@ extern "C" int ref_run(int coll, int nx, int ny, const float* params, int nparam
 '''
 
 
-def generate_source() -> str:
+def generate_source(real: str = "float") -> str:
     with open(os.path.join(REF_DIR, "MRT_GPU.py"), encoding="utf-8-sig") as fh:
         src = fh.read()
     rt = re.findall(r'funRT = """(.*?)"""', src, flags=re.S)
@@ -79,19 +83,24 @@ def generate_source() -> str:
         out.append(text)
     out.append(bc[0])
     out.append(DRIVER)
-    return "\n".join(out)
+    text = "\n".join(out)
+    if real != "float":
+        text = re.sub(r"\bfloat\b", real, text).replace("* 4", "* sizeof(%s)" % real)
+    return text
 
 
 def build(force: bool = False) -> str:
-    if os.path.exists(OUT) and not force:
-        return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    with tempfile.TemporaryDirectory(prefix="ref_kernels_") as tmp:
-        cu = os.path.join(tmp, "ref_kernels.cu")
-        with open(cu, "w") as fh:
-            fh.write(generate_source())
-        subprocess.check_call([NVCC, "-O2", "-w", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
-                               "-shared", "-o", OUT, cu])
+    for out, real in ((OUT, "float"), (OUT_F64, "double")):
+        if os.path.exists(out) and not force:
+            continue
+        with tempfile.TemporaryDirectory(prefix="ref_kernels_") as tmp:
+            cu = os.path.join(tmp, "ref_kernels.cu")
+            with open(cu, "w") as fh:
+                fh.write(generate_source(real))
+            # -fmad=false for the fp64 build: no contraction, i.e. the arithmetic the source text spells out
+            subprocess.check_call([NVCC, "-O2", "-w", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+                                   "-shared"] + (["-fmad=false"] if real == "double" else []) + ["-o", out, cu])
     return OUT
 
 

@@ -129,27 +129,29 @@ def ref_kernels_built() -> bool:
 
 
 def run_reference_kernels(nx: int, ny: int, Re: float, steps: int, collision: str = "MRT", turb: int = 0,
-                          uLB: float = 0.08):
+                          uLB: float = 0.08, dtype: str = "float32"):
     """Run funRT (+ funBC) of MRT_GPU.py for ``steps`` iterations exactly as the script does (fp32 device arrays in
     the [k][y][x] layout, init of :259-267 / :323-328, parameters of :63-91) and return ``(rho[x,y], u[2,x,y],
     fin[9,x,y])`` as the script would after its downloads and transposes (:755-760)."""
     import ctypes as C_
     from . import lbm_oracle as O
-    lib = C_.CDLL(REF_KERNELS_SO)
-    fp = C_.POINTER(C_.c_float)
+    # dtype="float64": the same kernel text with float -> double (oracle/build_ref_kernels.py)
+    npdt = np.float32 if dtype == "float32" else np.float64
+    lib = C_.CDLL(REF_KERNELS_SO if dtype == "float32" else REF_KERNELS_F64_SO)
+    fp = C_.POINTER(C_.c_float if dtype == "float32" else C_.c_double)
     lib.ref_run.argtypes = [C_.c_int, C_.c_int, C_.c_int, fp, C_.c_int, C_.c_int] + [fp] * 6
     nuLB = uLB * ny / Re                                       # MRT_GPU.py:63
     omega = 2.0 / (6. * nuLB + 1)                              # :65
     omegam = 1.0 / (0.5 + ((1.0 / 3.5) / ((1 / omega) - 0.5)))  # :82-84
     params = {"SRT": [uLB, omega, turb], "TRT": [uLB, omega, omegam, turb],
               "MRT": [uLB, omega, 1.0, 1.2, 1.2, turb]}[collision]      # :88-91 and the `%` tuples
-    P = np.asarray(params, dtype=np.float32)
+    P = np.asarray(params, dtype=npdt)
     _, vel, feq = O.init_fields(nx, ny, uLB)                   # :259-267 (fp64), then cast to fp32 (:298)
-    dev = lambda a: np.ascontiguousarray(np.swapaxes(a.astype(np.float32), -1, -2))     # [.., x, y] -> [.., y, x]
+    dev = lambda a: np.ascontiguousarray(np.swapaxes(a.astype(npdt), -1, -2))     # [.., x, y] -> [.., y, x]
     fin, ftemp, feq_g = dev(feq), dev(feq), dev(feq)
-    rho = np.ones((ny, nx), np.float32)
-    u = np.zeros((2, ny, nx), np.float32)
-    taus = np.full((ny, nx), 1.0 / omega, np.float32)
+    rho = np.ones((ny, nx), npdt)
+    u = np.zeros((2, ny, nx), npdt)
+    taus = np.full((ny, nx), 1.0 / omega, npdt)
     ptr = lambda a: a.ctypes.data_as(fp)
     rc = lib.ref_run({"SRT": 0, "TRT": 1, "MRT": 2}[collision], nx, ny, ptr(P), len(P), int(steps),
                      ptr(fin), ptr(ftemp), ptr(feq_g), ptr(rho), ptr(u), ptr(taus))

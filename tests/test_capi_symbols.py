@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_capi.SYMBOLS) == names
-    assert lib.lbm_abi_version() == 2
+    assert lib.lbm_abi_version() == 3
 
 
 def test_config_struct_matches_header_size():

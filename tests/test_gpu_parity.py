@@ -425,25 +425,40 @@ def test_tma_engine_parity(dtype):
         assert s.engine == "tma"
 
 
-@pytest.mark.parametrize("env", [{"LBM_B200_VEC_F64": "2", "LBM_B200_VEC_F32": "2"}, {"LBM_B200_VEC_F32": "1"},
-                                 {"LBM_B200_GRAPH": "0", "LBM_B200_PDL": "0"}, {"LBM_B200_FUSED2": "0"},
-                                 {"LBM_B200_FUSED2_TILE": "0"}])
-def test_kernel_variants_are_bit_identical(env, monkeypatch):
+@pytest.mark.parametrize("tuning", ["vec_f64=2,vec_f32=2", "vec_f32=1", "graph=0,pdl=0", "two_step=0", "slide=0,march=0",
+                                    "slide=0,march=0,tile=0", "slide_h=14", "slide_h=37", "slide_h=126", "slide=0",
+                                    "slide=0,march_variant=1", "slide=0,march_variant=2,march_h=8",
+                                    "slide=0,march_variant=4,march_h=16", "slide=0,march_variant=6,march_h=32",
+                                    "slide=0,march_h=37"])
+def test_kernel_variants_are_bit_identical(tuning, monkeypatch):
     """Every compiled data-movement variant (scalar / 2 / 4 nodes per thread, with and without graphs and programmatic
-    dependent launch) produces the same bits as the default configuration."""
+    dependent launch, one-step kernels, shared-memory two-step tiles, the sliding-window two-step kernel at several
+    segment heights, variants and segment heights of the marching two-step kernel) produces the same bits as the
+    default configuration."""
     import latticeboltzmannsimulations_b200 as L
-    # the last three are above the size threshold of the two-step (temporal blocking) kernel; 70 and 71 steps end on
-    # a macro-writing two-step launch and on a one-step launch respectively
+    # the later cases are above the size threshold of the two-step (temporal blocking) kernels; 70 and 71 steps end on
+    # a macro-writing two-step launch and on a one-step launch respectively; turb = 1 exercises the double-buffered
+    # Smagorinsky state of the marching kernel
     cases = [("float64", 200, 90, "MRT", False), ("float32", 131, 77, "SRT", False), ("float32", 96, 64, "MRT", True),
-             ("float64", 1000, 640, "MRT", False), ("float32", 1100, 600, "SRT", False), ("float64", 777, 801, "TRT", False)]
+             ("float64", 1000, 640, "MRT", False), ("float32", 1100, 600, "SRT", False), ("float64", 777, 801, "TRT", False),
+             ("float32", 1001, 640, "MRT", False), ("float64", 930, 700, "SRT", True), ("float32", 1030, 610, "MRT", True)]
+    monkeypatch.delenv("LBM_B200_TUNING", raising=False)
     ref = [L.run_cavity(nx, ny, 1000, steps=70 + (nx == 777), dtype=dt, collision=c, turb=t, return_f=True)
            for dt, nx, ny, c, t in cases]
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
+    monkeypatch.setenv("LBM_B200_TUNING", tuning)
     for (dt, nx, ny, c, t), want in zip(cases, ref):
         got = L.run_cavity(nx, ny, 1000, steps=70 + (nx == 777), dtype=dt, collision=c, turb=t, return_f=True)
         for a, b in zip(got, want):
-            assert np.array_equal(a, b), (env, dt, c)
+            assert np.array_equal(a, b), (tuning, dt, nx, ny, c, t)
+
+
+def test_tuning_keys_are_validated():
+    import latticeboltzmannsimulations_b200 as L
+    with L.CavitySolver(64, 64) as s:
+        s.set_tuning("march_h", 16)
+        for key, val in (("no_such_key", 1), ("march_variant", 99), ("vec_f32", 3), ("tile", 17)):
+            with pytest.raises(L.LBMError):
+                s.set_tuning(key, val)
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])

@@ -1,0 +1,24 @@
+"""Where does the marching two-step kernel differ from the one-step kernels?  (development aid)"""
+import sys
+import numpy as np
+sys.path.insert(0, ".")
+import latticeboltzmannsimulations_b200 as L
+
+def run(nx, ny, dt, coll, turb, steps, tuning):
+    with L.CavitySolver(nx, ny, 1, dt, coll, turb, tuning=tuning) as s:
+        s.set_reynolds(1000); s.init_equilibrium(); s.step(steps, write_macros=True)
+        rho, u = s.macros()
+        return rho, u, s.download_f()
+
+for (nx, ny, dt, coll, turb, steps) in [(777, 801, "float64", "TRT", False, 3), (777, 801, "float64", "TRT", False, 11),
+                                        (777, 801, "float64", "SRT", False, 11), (777, 801, "float64", "MRT", False, 11),
+                                        (777, 801, "float32", "TRT", False, 11), (1000, 640, "float64", "TRT", False, 11),
+                                        (930, 700, "float64", "SRT", True, 11), (1030, 610, "float32", "MRT", True, 11)]:
+    a = run(nx, ny, dt, coll, turb, steps, {"two_step": 0})
+    for tun in ({"slide_min_nodes": 0}, {"slide_min_nodes": 0, "slide_h": 37}, {"slide": 0, "march_min_nodes": 0}, {"slide": 0, "march": 0}):
+        b = run(nx, ny, dt, coll, turb, steps, tun)
+        d = np.abs(a[2] - b[2]).max(axis=0)
+        bad = np.argwhere(d > 0)
+        msg = "equal" if len(bad) == 0 else "%d nodes differ, max %.3e, x in [%d,%d], y in [%d,%d], first %s" % (
+            len(bad), d.max(), bad[:, 0].min(), bad[:, 0].max(), bad[:, 1].min(), bad[:, 1].max(), bad[:5].tolist())
+        print(nx, ny, dt, coll, turb, steps, tun, "->", msg, "| macros equal:", np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), flush=True)
