@@ -263,8 +263,10 @@ __device__ __forceinline__ void collide_trt_dev(T f[9], T drho, T rho, T ux, T u
 // Evaluated as f* = f - Minv * S * (m - m_eq) with M and Minv hand-factored (entries 0,+-1,+-2,+-4 / 1/4..1/36):
 // ~80 operations instead of two dense 9x9 products.  Rounding differs from the reference's "Minv * m*" form at the
 // 1e-16 level per step (measured 5e-14 in rho after 1000 steps at 96^2, Re 3200; tolerance 1e-12).
+// rho_given: the density entering the equilibrium moments when it is not the plain sum of the populations (lid row);
+// otherwise (use_given = false) it is summed here from the partial sums the transform needs anyway.
 template <typename T>
-__device__ __forceinline__ void collide_mrt(T f[9], T rho, T s_e, T s_eps, T s_q, T s_nu) {
+__device__ __forceinline__ void collide_mrt(T f[9], bool use_given, T rho_given, T s_e, T s_eps, T s_q, T s_nu) {
     const T p13 = f[1] + f[3], m13 = f[1] - f[3];
     const T p24 = f[2] + f[4], m24 = f[2] - f[4];
     const T s57 = f[5] + f[7], d57 = f[5] - f[7];
@@ -273,6 +275,7 @@ __device__ __forceinline__ void collide_mrt(T f[9], T rho, T s_e, T s_eps, T s_q
     const T jxd = d57 - d68, jyd = d57 + d68;
     const T pxy = s57 - s68;
     const T ab = p13 + p24;
+    const T rho = use_given ? rho_given : f[0] + (ab + dg);
     const T jx = m13 + jxd, jy = m24 + jyd;
     const T e = fm((T)-4, f[0], fm((T)2, dg, -ab));
     const T eps = fm((T)4, f[0], fm((T)-2, ab, dg));
@@ -322,11 +325,14 @@ __device__ __forceinline__ T smagorinsky_omega(const T f[9], T pi_prev, T rho_pr
 template <typename T, int COLL, bool NEED_U, bool TURB = false>
 __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left, bool right, bool lid, bool bot,
                                             T& rho_out, T& ux_out, T& uy_out, T omega_nu = (T)0, T* pi_out = nullptr) {
-    T rho, jx, jy;
-    moments_ref<T>(f, rho, jx, jy);
-    T ux = (T)0, uy = (T)0;
-    if (NEED_U || TURB || COLL != COLL_MRT) {      // u = j / rho as one reciprocal and two multiplications
-        const T inv = (T)1 / rho;
+    T rho = (T)0, ux = (T)0, uy = (T)0;
+    // MRT without output and without closure needs neither u nor (off the lid) the reference-order density: the
+    // collision sums rho from its own partial sums; rho_out is then only defined on the lid row
+    constexpr bool LEAN = COLL == COLL_MRT && !NEED_U && !TURB;
+    if (!LEAN) {
+        T jx, jy;
+        moments_ref<T>(f, rho, jx, jy);
+        const T inv = (T)1 / rho;                  // u = j / rho as one reciprocal and two multiplications
         ux = jx * inv;
         uy = jy * inv;
     }
@@ -346,7 +352,7 @@ __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left
         *pi_out = fe5 - fe6 + fe7 - fe8;
     }
     if (COLL == COLL_MRT) {
-        collide_mrt<T>(f, rho, r.s_e, r.s_eps, r.s_q, om);
+        collide_mrt<T>(f, !LEAN || lid, rho, r.s_e, r.s_eps, r.s_q, om);
     } else if (sizeof(T) == 4) {
         const T drho = drho_of<T>(f, lid);
         if (COLL == COLL_SRT) collide_srt_dev<T>(f, drho, rho, ux, uy, om);

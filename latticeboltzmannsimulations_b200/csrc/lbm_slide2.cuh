@@ -2,18 +2,20 @@
 //
 // A CTA owns a strip of TX columns (512 bytes per row) and slides down a segment of `seg_h` rows, R = 4 rows per
 // iteration:
-//   stage    the source rows of the NEXT-BUT-ONE iteration are copied global -> shared with 16-byte cp.async into one
-//            of two staging buffers [9][R][TX + 2A] (A = elements per 16 bytes: the halo chunk on either side), so
-//            that two iterations of loads are in flight per CTA without holding registers;
+//   stage    the source rows of the NEXT-BUT-ONE iteration are copied global -> shared by the bulk copy engine
+//            (cp.async.bulk, one 544-byte row per population and row, completion on an mbarrier) into one of two
+//            staging buffers [9][R][TX + 2A] (A = elements per 16 bytes: the halo chunk on either side): two
+//            iterations of loads are in flight per CTA, no register and no LSU instruction is spent on them;
 //   S1       sub-step 1 (state t -> t+1) on rows [s, s+R) x columns [x0-1, x0+TX]: every thread pulls its nine
 //            populations from the staging buffer (the x / y shifts are plain shared-memory offsets), applies the wall
 //            rule where needed, collides, and writes the post-collision populations into a rolling window of R+2 rows
 //            [9][R+2][TX+2] in shared memory;
 //   S2       sub-step 2 (t+1 -> t+2) on rows [s-1, s+R-1) x columns [x0, x0+TX) pulls from that window and stores
 //            with aligned, coalesced 512-byte rows.
-// Two block barriers per iteration (staging visible / window complete).  Redundant work: the two ring columns
-// (2 / TX of sub-step 1) and one row above and below the segment (2 / seg_h) -- against 29 % for the 64x8 tiles of
-// lbm_step_fused2 -- and no per-tile prologue: the loads of iteration i+2 overlap both sub-steps of iterations i, i+1.
+// Synchronisation per iteration: the "window free" barrier is split (every thread arrives on an mbarrier when its
+// sub-step 2 is done and waits only just before its sub-step-1 results are written, i.e. after the arithmetic), the
+// "window complete" barrier is an ordinary block barrier.  Redundant work: the two ring columns (2 / TX of sub-step 1)
+// and one row above and below the segment (2 / seg_h) -- against 29 % for the 64x8 tiles of lbm_step_fused2.
 // The per-node arithmetic is node_update()/wall_rule() of lbm_device.cuh: bit-identical to two one-step launches.
 #pragma once
 #include <cuda_runtime.h>
@@ -34,14 +36,40 @@ template <typename T> struct SlideCfg {
     static constexpr int STAGE = 9 * R * SW;              // elements per staging buffer
     static constexpr int WINDOW = 9 * WR * WW;
     static constexpr int SIDE = WW + 4;                   // lid density after sub-step 1 [WW], corner carries [4]
-    static constexpr size_t SMEM = (size_t)(2 * STAGE + WINDOW + SIDE) * sizeof(T);
+    static constexpr int COPIERS = 9 * R;                 // one bulk copy per (population, row) of a stage
+    static constexpr size_t DATA = (size_t)(2 * STAGE + WINDOW + SIDE) * sizeof(T);
+    static constexpr size_t BAR_OFF = (DATA + 15) / 16 * 16;       // three mbarriers: staging full [2], window free
+    static constexpr size_t SMEM = BAR_OFF + 3 * 8;
 };
 
-__device__ __forceinline__ void slide_cp16(unsigned dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ unsigned slide_sa(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void slide_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void slide_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void slide_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void slide_mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void slide_mbar_expect(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void slide_mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SLIDE_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SLIDE_DONE;\n"
+        "bra SLIDE_WAIT;\n"
+        "SLIDE_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// one row global -> shared through the bulk copy engine; bytes and both addresses are multiples of 16
+__device__ __forceinline__ void slide_bulk(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 
 // Apply the wall rule to the gathered populations of a (possibly) wall node; returns through f.
 template <typename T>
@@ -86,58 +114,57 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
     const Rates<T> rt(a.cav[b]);
     const T* carry_in = static_cast<const T*>(a.carry) + b * 4;
     const T* rl_in = static_cast<const T*>(a.rho_lid) + (long long)b * a.pitch;
-    const unsigned stg_sa = (unsigned)__cvta_generic_to_shared(stg);
+    const unsigned stg_sa = slide_sa(stg);
     // strip without wall columns whose staged halo chunks lie inside the row
     const bool xin = x0 >= A && x0 + TX + A <= a.nx;
 
-    // copy assignment, fixed for the whole segment: thread = (group g, chunk ch); it stages chunk ch of row j = g & 3
-    // of populations k = (g >> 2), (g >> 2) + 2, ...  (8 groups x 34 chunks = 272 of the 288 threads)
-    const int cg = tid / Cfg::CH, cch = tid - cg * Cfg::CH;
-    const int cj = cg & 3, ck0 = cg >> 2;
-    const bool copier = cg < 8;
-    const unsigned cdst = stg_sa + (unsigned)((cj * SW + cch * A) * E);      // + (buf * 9 + k) * R * SW * E
+    // barriers: staging buffer full [2] (COPIERS arrivals + the bytes of their copies), window free (NT arrivals)
+    const unsigned bar_full = slide_sa(slide_smem + Cfg::BAR_OFF);
+    const unsigned bar_free = bar_full + 16;
+    if (tid == 0) {
+        slide_mbar_init(bar_full, Cfg::COPIERS);
+        slide_mbar_init(bar_full + 8, Cfg::COPIERS);
+        slide_mbar_init(bar_free, NT);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // copy assignment, fixed for the whole segment: thread t < 9 R stages row j = t & 3 of population k = t >> 2
+    const int ck = tid >> 2, cj = tid & 3;
+    const int cdy = (ck == 2 || ck == 5 || ck == 6) ? 1 : ((ck == 4 || ck == 7 || ck == 8) ? -1 : 0);
 
     // ---- stage the source rows of the iteration whose first sub-step-1 row is s into buffer `buf` -----------------
     auto issue = [&](int s, int buf) {
-        if (s <= yb && copier) {
+        if (s <= yb && tid < Cfg::COPIERS) {
+            const unsigned bar = bar_full + 8 * buf;
             // interior block: rows s-1 .. s+R all exist in the main buffer (no wall row, no ghost row beyond)
             const int gy0 = a.y0 + s;
             const bool yin = gy0 - 1 >= 0 && gy0 + R <= a.ny - 1 && s - 1 >= -1 && s + R <= a.nyl;
-            const unsigned d0 = cdst + (unsigned)(buf * Cfg::STAGE * E);
+            const unsigned d0 = stg_sa + (unsigned)((((buf * 9 + ck) * R + cj) * SW) * E);
             if (xin && yin) {
-                const T* pb = src + (long long)(s + cj + 1) * pitch + (x0 - A + cch * A);     // population 0, row s + j
-                if (ck0 == 0) {
-                    slide_cp16(d0, pb);
-                    slide_cp16(d0 + 2 * R * SW * E, pb + 2 * P + pitch);
-                    slide_cp16(d0 + 4 * R * SW * E, pb + 4 * P - pitch);
-                    slide_cp16(d0 + 6 * R * SW * E, pb + 6 * P + pitch);
-                    slide_cp16(d0 + 8 * R * SW * E, pb + 8 * P - pitch);
-                } else {
-                    slide_cp16(d0 + 1 * R * SW * E, pb + P);
-                    slide_cp16(d0 + 3 * R * SW * E, pb + 3 * P);
-                    slide_cp16(d0 + 5 * R * SW * E, pb + 5 * P + pitch);
-                    slide_cp16(d0 + 7 * R * SW * E, pb + 7 * P - pitch);
-                }
+                slide_mbar_expect(bar, SW * E);
+                slide_bulk(d0, src + ck * P + (long long)(s + cj + cdy + 1) * pitch + (x0 - A), SW * E, bar);
             } else {
-                const T* g2top = static_cast<const T*>(a.ghost2) + (long long)b * 6 * a.pitch;   // second ghost rows
-                const T* g2bot = g2top + 3 * a.pitch;
-                const int col = x0 - A + cch * A;
-                if (col >= 0 && col < a.pitch && s + cj <= a.nyl) {      // chunk inside the stored row, row computed
-                    for (int k = ck0; k < 9; k += 2) {
-                        const int dy = (k == 2 || k == 5 || k == 6) ? 1 : ((k == 4 || k == 7 || k == 8) ? -1 : 0);
-                        int q = s + cj + dy;                               // local source row
-                        const int gq = a.y0 + q;
-                        if (gq < 0 || gq > a.ny - 1) q = s + cj;          // source row beyond a wall: never used, stay in bounds
-                        const T* p;
-                        if (q == -2) p = g2top + (k == 4 ? 0 : k == 7 ? 1 : 2) * pitch + col;
-                        else if (q == a.nyl + 1) p = g2bot + (k == 2 ? 0 : k == 5 ? 1 : 2) * pitch + col;
-                        else p = src + k * P + (long long)(q + 1) * pitch + col;
-                        slide_cp16(d0 + (unsigned)(k * R * SW * E), p);
-                    }
+                const int c0 = x0 - A < 0 ? 0 : x0 - A;                  // staged columns inside the stored row
+                const int c1 = x0 + TX + A > a.pitch ? a.pitch : x0 + TX + A;
+                int q = s + cj + cdy;                                    // local source row
+                const int gq = a.y0 + q;
+                if (gq < 0 || gq > a.ny - 1) q = s + cj;                // source row beyond a wall: never used, stay in bounds
+                if (s + cj > a.nyl || c1 <= c0) {                        // row not computed
+                    slide_mbar_arrive(bar);
+                } else {
+                    const T* g2top = static_cast<const T*>(a.ghost2) + (long long)b * 6 * a.pitch;   // second ghost rows
+                    const T* g2bot = g2top + 3 * a.pitch;
+                    const T* p;
+                    if (q == -2) p = g2top + (ck == 4 ? 0 : ck == 7 ? 1 : 2) * pitch;
+                    else if (q == a.nyl + 1) p = g2bot + (ck == 2 ? 0 : ck == 5 ? 1 : 2) * pitch;
+                    else p = src + ck * P + (long long)(q + 1) * pitch;
+                    const unsigned bytes = (unsigned)((c1 - c0) * E);
+                    slide_mbar_expect(bar, bytes);
+                    slide_bulk(d0 + (unsigned)((c0 - (x0 - A)) * E), p + c0, bytes, bar);
                 }
             }
         }
-        slide_commit();
     };
 
     // node assignment, fixed for the whole segment
@@ -156,12 +183,13 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
     const int s0 = ya - 1;
     issue(s0, 0);
     issue(s0 + R, 1);
+    slide_mbar_arrive(bar_free);                                   // the window is free for the first iteration
     int wbase = 0;                                                 // window slot of sub-step-1 row s
     int buf = 0;
-    for (int s = s0; s <= yb; s += R) {
-        slide_wait<1>();                                           // this thread's copies of the current buffer have landed
-        __syncthreads();                                           // ... and everybody else's; sub-step 2 of the previous
-                                                                   // iteration has finished reading the window
+    unsigned it = 0;                                               // iteration count: parities of the barriers
+    for (int s = s0; s <= yb; s += R, ++it) {
+        slide_mbar_wait(bar_full + 8 * buf, (it >> 1) & 1);        // the staged rows of this iteration have landed
+        bool window_free = false;                                  // waited for sub-step 2 of the previous iteration?
         const T* S = stg + buf * Cfg::STAGE;
         const int gys = a.y0 + s;
         // no wall node among the sub-step-1 nodes of this iteration (rows s .. s+R-1, columns x0-1 .. x0+TX), all exist
@@ -208,9 +236,14 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
                 node_update<T, COLL, false>(f, rt, left, right, lid, bot, rho, ux, uy);
                 if (lid) rl1[lx] = rho;
             }
+            if (!window_free) {                                    // everybody's sub-step 2 of the previous iteration
+                slide_mbar_wait(bar_free, it & 1);                 // has read the window rows overwritten now
+                window_free = true;
+            }
 #pragma unroll
             for (int k = 0; k < 9; ++k) w[k * WR * WW] = f[k];
         }
+        if (!window_free) slide_mbar_wait(bar_free, it & 1);       // (threads without a sub-step-1 node)
         __syncthreads();                                           // window rows [s, s+R) complete; staging buffer free
         issue(s + 2 * R, buf);
         // no wall node among the sub-step-2 nodes of this iteration (rows s-1 .. s+R-2, columns x0 .. x0+TX-1), all stored
@@ -273,11 +306,11 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
                 static_cast<T*>(a.uy)[m] = uy;
             }
         }
+        slide_mbar_arrive(bar_free);                               // this thread is done reading the window
         wbase += R;
         wbase = wbase >= WR ? wbase - WR : wbase;
         buf ^= 1;
     }
-    slide_wait<0>();
 }
 
 }  // namespace lbm
