@@ -73,6 +73,34 @@ template <typename T> __device__ __forceinline__ T w_diag() { return (T)(1.0 / 3
 __device__ __forceinline__ float fm(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ double fm(double a, double b, double c) { return __fma_rn(a, b, c); }
 
+// ---- two fp32 nodes per thread: Blackwell packed arithmetic ---------------------------------------------------------
+// sm_100 adds packed fp32 instructions (FADD2 / FMUL2 / FFMA2: two IEEE round-to-nearest results per lane and
+// instruction).  f32x2 runs the SAME templated node arithmetic below on two x-adjacent nodes at once: every operator
+// maps to one packed instruction whose two halves are exactly what the scalar code computes, so a kernel may mix
+// packed and scalar nodes and stay bit-identical (a - b is fma(b, -1, a): b * -1 is exact; -a is a * -1).
+struct f32x2 {
+    float2 v;
+    __device__ __forceinline__ f32x2() {}
+    __device__ __forceinline__ explicit f32x2(float a) : v(make_float2(a, a)) {}
+    __device__ __forceinline__ explicit f32x2(double a) : v(make_float2((float)a, (float)a)) {}
+    __device__ __forceinline__ explicit f32x2(int a) : v(make_float2((float)a, (float)a)) {}
+    __device__ __forceinline__ f32x2(float a, float b) : v(make_float2(a, b)) {}
+    __device__ __forceinline__ explicit f32x2(float2 a) : v(a) {}
+};
+__device__ __forceinline__ f32x2 operator+(f32x2 a, f32x2 b) { return f32x2(__fadd2_rn(a.v, b.v)); }
+__device__ __forceinline__ f32x2 operator*(f32x2 a, f32x2 b) { return f32x2(__fmul2_rn(a.v, b.v)); }
+__device__ __forceinline__ f32x2 operator-(f32x2 a, f32x2 b) { return f32x2(__ffma2_rn(b.v, make_float2(-1.0f, -1.0f), a.v)); }
+__device__ __forceinline__ f32x2 operator-(f32x2 a) { return f32x2(__fmul2_rn(a.v, make_float2(-1.0f, -1.0f))); }
+__device__ __forceinline__ f32x2 operator/(f32x2 a, f32x2 b) { return f32x2(a.v.x / b.v.x, a.v.y / b.v.y); }
+__device__ __forceinline__ f32x2 fm(f32x2 a, f32x2 b, f32x2 c) { return f32x2(__ffma2_rn(a.v, b.v, c.v)); }
+using ::sqrt;       // keep the scalar overloads visible next to the packed ones
+using ::fabs;
+__device__ __forceinline__ f32x2 sqrt(f32x2 a) { return f32x2(sqrtf(a.v.x), sqrtf(a.v.y)); }
+__device__ __forceinline__ f32x2 fabs(f32x2 a) { return f32x2(fabsf(a.v.x), fabsf(a.v.y)); }
+// fp32 takes the deviation forms of SRT / TRT (see below); the packed type is fp32
+template <typename T> struct is_fp32 { static constexpr bool value = sizeof(T) == 4; };
+template <> struct is_fp32<f32x2> { static constexpr bool value = true; };
+
 // feq_k = rho*t_k*(1. + 3.0*cu + 9*0.5*cu*cu - 3.0*0.5*usqr)   (MRT_GPU.py:651), Horner in cu; rt = rho * t_k.
 template <typename T>
 __device__ __forceinline__ T feq_one(T rt, T cu, T usqr) {
@@ -353,7 +381,7 @@ __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left
     }
     if (COLL == COLL_MRT) {
         collide_mrt<T>(f, !LEAN || lid, rho, r.s_e, r.s_eps, r.s_q, om);
-    } else if (sizeof(T) == 4) {
+    } else if (is_fp32<T>::value) {
         const T drho = drho_of<T>(f, lid);
         if (COLL == COLL_SRT) collide_srt_dev<T>(f, drho, rho, ux, uy, om);
         else collide_trt_dev<T>(f, drho, rho, ux, uy, om, r.omegam);

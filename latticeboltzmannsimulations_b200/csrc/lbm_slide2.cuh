@@ -30,12 +30,15 @@ template <typename T> struct SlideCfg {
     static constexpr int R = 4;                           // rows per iteration
     static constexpr int SW = TX + 2 * A;                 // staged columns [x0 - A, x0 + TX + A)
     static constexpr int CH = SW / A;                     // 16-byte chunks per staged row (34)
-    static constexpr int WW = TX + 2;                     // window columns [x0 - 1, x0 + TX + 1)
+    static constexpr int NV = 8 / (int)sizeof(T);         // nodes per thread and sub-step: 1 fp64 / 2 fp32 (packed f32x2)
+    static constexpr int WOFF = NV - 1;                   // window column of x0-1: keeps the pairs 8-byte aligned
+    static constexpr int WW = TX + 2 + 2 * WOFF;          // window columns [x0 - 1, x0 + TX + 1) (+ alignment padding)
     static constexpr int WR = R + 2;                      // window rows
-    static constexpr int NT = 288;                        // threads: 9 warps >= R * WW = 264 sub-step-1 nodes (fp64)
+    static constexpr int ITEMS = R * 64;                  // main items per sub-step: R rows x 64 (pairs of) columns
+    static constexpr int NT = 288;                        // threads: 9 warps >= ITEMS + 2 R ring nodes = 264
     static constexpr int STAGE = 9 * R * SW;              // elements per staging buffer
     static constexpr int WINDOW = 9 * WR * WW;
-    static constexpr int SIDE = WW + 4;                   // lid density after sub-step 1 [WW], corner carries [4]
+    static constexpr int SIDE = TX + 2 + 4;               // lid density after sub-step 1 [TX + 2], corner carries [4]
     static constexpr int COPIERS = 9 * R;                 // one bulk copy per (population, row) of a stage
     static constexpr size_t DATA = (size_t)(2 * STAGE + WINDOW + SIDE) * sizeof(T);
     static constexpr size_t BAR_OFF = (DATA + 15) / 16 * 16;       // three mbarriers: staging full [2], window free
@@ -85,19 +88,37 @@ __device__ __forceinline__ void slide_walls(T f[9], bool left, bool right, bool 
     if (slot >= 0) carry_keep[slot] = corner_value<T>(f, slot);
 }
 
+// One item = NV x-adjacent nodes of a row handled by one thread: a double, or two floats as a packed f32x2.
+template <typename T> struct SlideItem;
+template <> struct SlideItem<double> {
+    using AT = double;
+    static __device__ __forceinline__ AT ld(const double* p) { return *p; }                    // nodes at p[0..NV)
+    static __device__ __forceinline__ AT ldx(const double* p, int dx) { return p[dx]; }        // shifted by dx = +-1
+    static __device__ __forceinline__ void st(double* p, AT v) { *p = v; }
+    static __device__ __forceinline__ double get(AT v, int) { return v; }
+};
+template <> struct SlideItem<float> {
+    using AT = f32x2;
+    static __device__ __forceinline__ AT ld(const float* p) { return f32x2(*reinterpret_cast<const float2*>(p)); }
+    static __device__ __forceinline__ AT ldx(const float* p, int dx) { return f32x2(p[dx], p[dx + 1]); }
+    static __device__ __forceinline__ void st(float* p, AT v) { *reinterpret_cast<float2*>(p) = v.v; }
+    static __device__ __forceinline__ float get(AT v, int i) { return i ? v.v.y : v.v.x; }
+};
+
 template <typename T, int COLL, bool MACROS, int MINB>
 __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const StepArgs a) {
     using Cfg = SlideCfg<T>;
     constexpr int TX = Cfg::TX, A = Cfg::A, R = Cfg::R, SW = Cfg::SW, WW = Cfg::WW, WR = Cfg::WR, NT = Cfg::NT;
+    constexpr int NV = Cfg::NV, WOFF = Cfg::WOFF;
     constexpr int E = (int)sizeof(T);
-    constexpr int P1 = (R * WW + NT - 1) / NT;                     // passes of sub-step 1 over the thread block
-    constexpr int P2 = (R * TX + NT - 1) / NT;                     // passes of sub-step 2
-    static_assert(R == 4, "the copy assignment below fixes the staged row per thread as (group & 3)");
+    using Item = SlideItem<T>;
+    using AT = typename Item::AT;
+    static_assert(R == 4, "the copy assignment below fixes the staged row per thread as (tid & 3)");
     extern __shared__ __align__(16) unsigned char slide_smem[];
     T* stg = reinterpret_cast<T*>(slide_smem);                     // [2][9][R][SW]
     T* win = stg + 2 * Cfg::STAGE;                                 // [9][WR][WW]
-    T* rl1 = win + Cfg::WINDOW;                                    // [WW] lid density after sub-step 1
-    T* c1 = rl1 + WW;                                              // [4]  corner carries after sub-step 1
+    T* rl1 = win + Cfg::WINDOW;                                    // [TX + 2] lid density after sub-step 1
+    T* c1 = rl1 + TX + 2;                                          // [4]  corner carries after sub-step 1
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int b = blockIdx.z;
@@ -112,6 +133,7 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
     const long long P = a.plane;
     const long long pitch = a.pitch;
     const Rates<T> rt(a.cav[b]);
+    const Rates<AT> rta(a.cav[b]);                                 // the same rates for the item arithmetic
     const T* carry_in = static_cast<const T*>(a.carry) + b * 4;
     const T* rl_in = static_cast<const T*>(a.rho_lid) + (long long)b * a.pitch;
     const unsigned stg_sa = slide_sa(stg);
@@ -167,18 +189,70 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
         }
     };
 
-    // node assignment, fixed for the whole segment
-    int j1[P1], lx1[P1], j2[P2], tx2[P2];
+    // item assignment, fixed for the whole segment: thread t < ITEMS owns row j = t / 64 and the NV nodes starting at
+    // column x0 + NV (t % 64) in both sub-steps; threads ITEMS .. ITEMS + 2R - 1 own one ring node each in sub-step 1
+    const bool main_item = tid < Cfg::ITEMS;
+    const bool ring_item = !main_item && tid < Cfg::ITEMS + 2 * R;
+    const int ij = main_item ? tid >> 6 : (tid - Cfg::ITEMS) >> 1;                 // row within the block
+    const int ilx = main_item ? NV * (tid & 63) + 1 : ((tid & 1) ? TX + 1 : 0);    // sub-step-1 column index (x0 - 1 + ilx)
+    const int itx = NV * (tid & 63);                                               // sub-step-2 column (x0 + itx)
+
+    // one sub-step-1 node through the general (wall-aware) path: staged populations -> window
+    auto s1_node = [&](const T* S, int s, int lx, T* w) {
+        const int q = s + ij, x = x0 - 1 + lx;
+        const int y = a.y0 + q;
+        if (q > yb || x < 0 || x >= a.nx || y < 0 || y >= a.ny) return;
+        const bool left = x == 0, right = x == a.nx - 1, lid = y == 0, bot = y == a.ny - 1;
+        const T* c = S + ij * SW + lx + (A - 1);                   // this node in population 0's staged rows
+        T f[9];
+        f[0] = c[0];
+        f[1] = c[1 * R * SW - 1];
+        f[2] = c[2 * R * SW];
+        f[3] = c[3 * R * SW + 1];
+        f[4] = c[4 * R * SW];
+        f[5] = c[5 * R * SW - 1];
+        f[6] = c[6 * R * SW + 1];
+        f[7] = c[7 * R * SW + 1];
+        f[8] = c[8 * R * SW - 1];
+        if (left || right || lid || bot)
+            slide_walls<T>(f, left, right, lid, bot, lid ? rl_in[x] : (T)1, rt.uLB, carry_in, c1);
+        T rho, ux, uy;
+        node_update<T, COLL, false>(f, rt, left, right, lid, bot, rho, ux, uy);
+        if (lid) rl1[lx] = rho;
 #pragma unroll
-    for (int p = 0; p < P1; ++p) {
-        const int n = tid + p * NT;
-        j1[p] = n / WW; lx1[p] = n - j1[p] * WW;
-    }
+        for (int k = 0; k < 9; ++k) w[k * WR * WW] = f[k];
+    };
+    // one sub-step-2 node through the general path: window -> global
+    auto s2_node = [&](int s, int tx, const T* pc, const T* pu, const T* pd) {
+        const int yl = s - 1 + ij, x = x0 + tx;
+        if (yl < ya || yl >= yb || x >= a.nx) return;
+        const int y = a.y0 + yl;
+        const bool left = x == 0, right = x == a.nx - 1, lid = y == 0, bot = y == a.ny - 1;
+        T f[9];
+        f[0] = pc[0];
+        f[1] = pc[1 * WR * WW - 1];
+        f[3] = pc[3 * WR * WW + 1];
+        f[2] = pd[2 * WR * WW];
+        f[5] = pd[5 * WR * WW - 1];
+        f[6] = pd[6 * WR * WW + 1];
+        f[4] = pu[4 * WR * WW];
+        f[7] = pu[7 * WR * WW + 1];
+        f[8] = pu[8 * WR * WW - 1];
+        if (left || right || lid || bot)
+            slide_walls<T>(f, left, right, lid, bot, lid ? rl1[tx + 1] : (T)1, rt.uLB, c1, static_cast<T*>(a.carry_out) + b * 4);
+        T rho, ux, uy;
+        node_update<T, COLL, MACROS>(f, rt, left, right, lid, bot, rho, ux, uy);
+        if (lid) static_cast<T*>(a.rho_lid_out)[(long long)b * a.pitch + x] = rho;
+        T* d = dst + (long long)(yl + 1) * pitch + x;
 #pragma unroll
-    for (int p = 0; p < P2; ++p) {
-        const int n = tid + p * NT;
-        j2[p] = n / TX; tx2[p] = n - j2[p] * TX;
-    }
+        for (int k = 0; k < 9; ++k) d[k * P] = f[k];
+        if (MACROS) {
+            const long long m = (long long)b * a.mplane + (long long)yl * pitch + x;
+            static_cast<T*>(a.rho)[m] = rho;
+            static_cast<T*>(a.ux)[m] = ux;
+            static_cast<T*>(a.uy)[m] = uy;
+        }
+    };
 
     const int s0 = ya - 1;
     issue(s0, 0);
@@ -189,121 +263,82 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
     unsigned it = 0;                                               // iteration count: parities of the barriers
     for (int s = s0; s <= yb; s += R, ++it) {
         slide_mbar_wait(bar_full + 8 * buf, (it >> 1) & 1);        // the staged rows of this iteration have landed
-        bool window_free = false;                                  // waited for sub-step 2 of the previous iteration?
         const T* S = stg + buf * Cfg::STAGE;
         const int gys = a.y0 + s;
-        // no wall node among the sub-step-1 nodes of this iteration (rows s .. s+R-1, columns x0-1 .. x0+TX), all exist
-        const bool inner1 = x0 - 1 > 0 && x0 + TX < a.nx - 1 && gys > 0 && gys + R - 1 < a.ny - 1 && s + R - 1 <= yb;
         // ---- sub-step 1: rows [s, s+R) x columns [x0-1, x0+TX] -> window ----
+        // no wall node among the main items of this iteration (rows s .. s+R-1, columns x0 .. x0+TX-1), all exist
+        const bool inner1 = x0 > 0 && x0 + TX - 1 < a.nx - 1 && gys > 0 && gys + R - 1 < a.ny - 1 && s + R - 1 <= yb;
+        int ws = wbase + ij;
+        ws = ws >= WR ? ws - WR : ws;
+        T* w = win + ws * WW + ilx + WOFF;
+        if (main_item && inner1) {
+            const T* c = S + ij * SW + ilx + (A - 1);              // first node of the item in population 0's staged rows
+            AT f[9];
+            f[0] = Item::ld(c);
+            f[1] = Item::ldx(c + 1 * R * SW, -1);
+            f[2] = Item::ld(c + 2 * R * SW);
+            f[3] = Item::ldx(c + 3 * R * SW, 1);
+            f[4] = Item::ld(c + 4 * R * SW);
+            f[5] = Item::ldx(c + 5 * R * SW, -1);
+            f[6] = Item::ldx(c + 6 * R * SW, 1);
+            f[7] = Item::ldx(c + 7 * R * SW, 1);
+            f[8] = Item::ldx(c + 8 * R * SW, -1);
+            AT rho, ux, uy;
+            node_update<AT, COLL, false>(f, rta, false, false, false, false, rho, ux, uy);
+            slide_mbar_wait(bar_free, it & 1);                     // everybody's sub-step 2 of the previous iteration has
+#pragma unroll                                                     // read the window rows overwritten now
+            for (int k = 0; k < 9; ++k) Item::st(w + k * WR * WW, f[k]);
+        } else {
+            slide_mbar_wait(bar_free, it & 1);
+            if (main_item) {
 #pragma unroll
-        for (int p = 0; p < P1; ++p) {
-            const int j = j1[p], lx = lx1[p];
-            if (j >= R) continue;
-            const T* c = S + j * SW + lx + (A - 1);                // this node in population 0's staged rows
-            int ws = wbase + j;
-            ws = ws >= WR ? ws - WR : ws;
-            T* w = win + ws * WW + lx;
-            T f[9];
-            if (inner1) {
-                f[0] = c[0];
-                f[1] = c[1 * R * SW - 1];
-                f[2] = c[2 * R * SW];
-                f[3] = c[3 * R * SW + 1];
-                f[4] = c[4 * R * SW];
-                f[5] = c[5 * R * SW - 1];
-                f[6] = c[6 * R * SW + 1];
-                f[7] = c[7 * R * SW + 1];
-                f[8] = c[8 * R * SW - 1];
-                T rho, ux, uy;
-                node_update<T, COLL, false>(f, rt, false, false, false, false, rho, ux, uy);
-            } else {
-                const int q = s + j, x = x0 - 1 + lx;
-                const int y = a.y0 + q;
-                if (q > yb || x < 0 || x >= a.nx || y < 0 || y >= a.ny) continue;
-                const bool left = x == 0, right = x == a.nx - 1, lid = y == 0, bot = y == a.ny - 1;
-                f[0] = c[0];
-                f[1] = c[1 * R * SW - 1];
-                f[2] = c[2 * R * SW];
-                f[3] = c[3 * R * SW + 1];
-                f[4] = c[4 * R * SW];
-                f[5] = c[5 * R * SW - 1];
-                f[6] = c[6 * R * SW + 1];
-                f[7] = c[7 * R * SW + 1];
-                f[8] = c[8 * R * SW - 1];
-                if (left || right || lid || bot)
-                    slide_walls<T>(f, left, right, lid, bot, lid ? rl_in[x] : (T)1, rt.uLB, carry_in, c1);
-                T rho, ux, uy;
-                node_update<T, COLL, false>(f, rt, left, right, lid, bot, rho, ux, uy);
-                if (lid) rl1[lx] = rho;
+                for (int v = 0; v < NV; ++v) s1_node(S, s, ilx + v, w + v);
+            } else if (ring_item) {
+                s1_node(S, s, ilx, w);
             }
-            if (!window_free) {                                    // everybody's sub-step 2 of the previous iteration
-                slide_mbar_wait(bar_free, it & 1);                 // has read the window rows overwritten now
-                window_free = true;
-            }
-#pragma unroll
-            for (int k = 0; k < 9; ++k) w[k * WR * WW] = f[k];
         }
-        if (!window_free) slide_mbar_wait(bar_free, it & 1);       // (threads without a sub-step-1 node)
         __syncthreads();                                           // window rows [s, s+R) complete; staging buffer free
         issue(s + 2 * R, buf);
-        // no wall node among the sub-step-2 nodes of this iteration (rows s-1 .. s+R-2, columns x0 .. x0+TX-1), all stored
+        // ---- sub-step 2: rows [s-1, s+R-1) x columns [x0, x0+TX) <- window ----
+        // no wall node among them, all inside the segment
         const bool inner2 = x0 > 0 && x0 + TX - 1 < a.nx - 1 && gys - 1 > 0 && gys + R - 2 < a.ny - 1 && s - 1 >= ya &&
                             s + R - 2 < yb;
-        // ---- sub-step 2: rows [s-1, s+R-1) x columns [x0, x0+TX) <- window ----
-#pragma unroll
-        for (int p = 0; p < P2; ++p) {
-            const int j = j2[p], tx = tx2[p];
-            if (j >= R) continue;
-            const int yl = s - 1 + j, x = x0 + tx;
-            int wc = wbase + j - 1;                                // window slot of row yl, of yl - 1 and of yl + 1
+        if (main_item) {
+            int wc = wbase + ij - 1;                               // window slot of row yl, of yl - 1 and of yl + 1
             wc = wc < 0 ? wc + WR : (wc >= WR ? wc - WR : wc);
             int wu = wc - 1;
             wu = wu < 0 ? wu + WR : wu;
             int wd = wc + 1;
             wd = wd >= WR ? wd - WR : wd;
-            const T* pc = win + wc * WW + tx + 1;
-            const T* pu = win + wu * WW + tx + 1;
-            const T* pd = win + wd * WW + tx + 1;
-            T f[9];
-            T rho, ux, uy;
+            const T* pc = win + wc * WW + itx + 1 + WOFF;
+            const T* pu = win + wu * WW + itx + 1 + WOFF;
+            const T* pd = win + wd * WW + itx + 1 + WOFF;
             if (inner2) {
-                f[0] = pc[0];
-                f[1] = pc[1 * WR * WW - 1];
-                f[3] = pc[3 * WR * WW + 1];
-                f[2] = pd[2 * WR * WW];
-                f[5] = pd[5 * WR * WW - 1];
-                f[6] = pd[6 * WR * WW + 1];
-                f[4] = pu[4 * WR * WW];
-                f[7] = pu[7 * WR * WW + 1];
-                f[8] = pu[8 * WR * WW - 1];
-                node_update<T, COLL, MACROS>(f, rt, false, false, false, false, rho, ux, uy);
-            } else {
-                if (yl < ya || yl >= yb || x >= a.nx) continue;
-                const int y = a.y0 + yl;
-                const bool left = x == 0, right = x == a.nx - 1, lid = y == 0, bot = y == a.ny - 1;
-                f[0] = pc[0];
-                f[1] = pc[1 * WR * WW - 1];
-                f[3] = pc[3 * WR * WW + 1];
-                f[2] = pd[2 * WR * WW];
-                f[5] = pd[5 * WR * WW - 1];
-                f[6] = pd[6 * WR * WW + 1];
-                f[4] = pu[4 * WR * WW];
-                f[7] = pu[7 * WR * WW + 1];
-                f[8] = pu[8 * WR * WW - 1];
-                if (left || right || lid || bot)
-                    slide_walls<T>(f, left, right, lid, bot, lid ? rl1[tx + 1] : (T)1, rt.uLB, c1,
-                                   static_cast<T*>(a.carry_out) + b * 4);
-                node_update<T, COLL, MACROS>(f, rt, left, right, lid, bot, rho, ux, uy);
-                if (lid) static_cast<T*>(a.rho_lid_out)[(long long)b * a.pitch + x] = rho;
-            }
-            T* d = dst + (long long)(yl + 1) * pitch + x;
+                AT f[9];
+                f[0] = Item::ld(pc);
+                f[1] = Item::ldx(pc + 1 * WR * WW, -1);
+                f[3] = Item::ldx(pc + 3 * WR * WW, 1);
+                f[2] = Item::ld(pd + 2 * WR * WW);
+                f[5] = Item::ldx(pd + 5 * WR * WW, -1);
+                f[6] = Item::ldx(pd + 6 * WR * WW, 1);
+                f[4] = Item::ld(pu + 4 * WR * WW);
+                f[7] = Item::ldx(pu + 7 * WR * WW, 1);
+                f[8] = Item::ldx(pu + 8 * WR * WW, -1);
+                AT rho, ux, uy;
+                node_update<AT, COLL, MACROS>(f, rta, false, false, false, false, rho, ux, uy);
+                const int yl = s - 1 + ij;
+                T* d = dst + (long long)(yl + 1) * pitch + (x0 + itx);
 #pragma unroll
-            for (int k = 0; k < 9; ++k) d[k * P] = f[k];
-            if (MACROS) {
-                const long long m = (long long)b * a.mplane + (long long)yl * pitch + x;
-                static_cast<T*>(a.rho)[m] = rho;
-                static_cast<T*>(a.ux)[m] = ux;
-                static_cast<T*>(a.uy)[m] = uy;
+                for (int k = 0; k < 9; ++k) Item::st(d + k * P, f[k]);
+                if (MACROS) {
+                    const long long m = (long long)b * a.mplane + (long long)yl * pitch + (x0 + itx);
+                    Item::st(static_cast<T*>(a.rho) + m, rho);
+                    Item::st(static_cast<T*>(a.ux) + m, ux);
+                    Item::st(static_cast<T*>(a.uy) + m, uy);
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) s2_node(s, itx + v, pc + v, pu + v, pd + v);
             }
         }
         slide_mbar_arrive(bar_free);                               // this thread is done reading the window
