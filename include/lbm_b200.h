@@ -95,9 +95,9 @@ int lbm_get_layout(lbm_handle_t h, lbm_layout_t* out);
  *   "two_step"            0 = one lattice step per launch only (default 1: temporal blocking where it pays)
  *   "two_step_min_nodes"  smallest batch x nx x ny that uses a two-step kernel (default 10000)
  *   "slide"               0 = never use the sliding-window two-step kernel (default 1)
- *   "slide_min_nodes"     smallest batch x nx x ny that uses it instead of the shared-memory tiles (default 600000)
+ *   "slide_min_nodes"     smallest batch x nx x ny that uses it instead of the shared-memory tiles (default 2000000)
  *   "slide_h"             rows per segment of the sliding-window kernel, 0 = automatic
- *   "march"               0 = never use the marching two-step kernel (default 1; it serves turb = 1)
+ *   "march"               1 = use the marching two-step kernel (default 0; the only two-step kernel for turb = 1)
  *   "march_min_nodes"     smallest batch x nx x ny that uses it (default 600000)
  *   "march_variant"       compiled (nodes per lane, register budget) variant, 0 = shipped default
  *   "march_h"             rows per segment, 0 = automatic

@@ -61,9 +61,11 @@ static int fail(int code, const std::string& msg) {
 // From here the marching two-step kernel (lbm_march2.cuh: one warp per x-strip segment, rolling register window)
 // replaces the shared-memory tiles; it also covers the Smagorinsky closure and batches with frozen cavities.
 #define LBM_MARCH_MIN_NODES 600000
-// The sliding-window two-step kernel (lbm_slide2.cuh: one CTA per column strip, cp.async double-buffered source rows)
-// takes over from the tiles at the same size; the marching kernel then only serves the Smagorinsky closure.
-#define LBM_SLIDE_MIN_NODES 600000
+// The sliding-window two-step kernel (lbm_slide2.cuh: one CTA per column strip, bulk-copy double-buffered source rows)
+// takes over where its segments fill the machine (tools/size_sweep2.py: 1024^2 tiles 63 545 / sliding 59 332 MLUPS fp64,
+// 2048^2 70 677 / 74 571, 32 x 384^2 66 741 / 70 942; fp32 2048^2 100 744 / 125 098); the marching kernel then only
+// serves the Smagorinsky closure.
+#define LBM_SLIDE_MIN_NODES 2000000
 
 // ------------------------------------------------------------------------------------------------------------
 // solver object
@@ -115,7 +117,7 @@ struct lbm_solver {
     int side = 0;              // which half of the double-buffered rho_lid / carry arrays is current
     int fused2_tile = -1;      // tile-shape variant of the fused kernel (-1 = per-dtype default)
     long long fused2_min_nodes = LBM_FUSED2_MIN_NODES;
-    int use_march = 1;         // marching two-step kernel for large cavities / batches
+    int use_march = 0;         // marching two-step kernel (optional: slower than the one-step kernels with turb = 1)
     int march_variant = 0;     // compiled (nodes per lane, register budget) variant, 0 = shipped default
     int march_h = 0;           // rows per segment, 0 = chosen from the number of work items
     long long march_min_nodes = LBM_MARCH_MIN_NODES;
@@ -375,9 +377,8 @@ static int two_step_kind(const lbm_solver* s) {
     if (s->use_march && nodes >= s->march_min_nodes && (!s->cfg.turb || whole)) return TWO_MARCH;
     // shared-memory tiles: no closure, no frozen cavities
     if (s->cfg.turb || s->active) return TWO_NONE;
-    // fp32 gains less from the tiles (ALU-bound) and loses on narrow cavities: 8 x 32 cavities of 384^2 ran at
-    // 666 537 MLUPS with them against 690 216 without
-    if (s->esz == 4 && s->cfg.nx < 1024) return TWO_NONE;
+    // fp32 never gains from the tiles (ALU-bound): 1024^2 one-step 107 088 / tiles 98 466 MLUPS, narrower cavities alike
+    if (s->esz == 4 && s->fused2_tile < 0) return TWO_NONE;
     if (s->fused2_tile < 0 && nodes >= LBM_FUSED2_SMALL_NODES && nodes < LBM_FUSED2_LARGE_NODES) return TWO_NONE;
     return TWO_TILE;
 }

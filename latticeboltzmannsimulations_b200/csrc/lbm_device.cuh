@@ -292,7 +292,8 @@ __device__ __forceinline__ void collide_trt_dev(T f[9], T drho, T rho, T ux, T u
 // ~80 operations instead of two dense 9x9 products.  Rounding differs from the reference's "Minv * m*" form at the
 // 1e-16 level per step (measured 5e-14 in rho after 1000 steps at 96^2, Re 3200; tolerance 1e-12).
 // rho_given: the density entering the equilibrium moments when it is not the plain sum of the populations (lid row);
-// otherwise (use_given = false) it is summed here from the partial sums the transform needs anyway.
+// otherwise (use_given = false) it is summed here from the partial sums the transform needs anyway -- always, so that a
+// step gives the same bits whether or not it also writes rho / u (which carry the reference-order sum).
 template <typename T>
 __device__ __forceinline__ void collide_mrt(T f[9], bool use_given, T rho_given, T s_e, T s_eps, T s_q, T s_nu) {
     const T p13 = f[1] + f[3], m13 = f[1] - f[3];
@@ -380,7 +381,7 @@ __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left
         *pi_out = fe5 - fe6 + fe7 - fe8;
     }
     if (COLL == COLL_MRT) {
-        collide_mrt<T>(f, !LEAN || lid, rho, r.s_e, r.s_eps, r.s_q, om);
+        collide_mrt<T>(f, lid, rho, r.s_e, r.s_eps, r.s_q, om);     // off the lid the same density with or without output
     } else if (is_fp32<T>::value) {
         const T drho = drho_of<T>(f, lid);
         if (COLL == COLL_SRT) collide_srt_dev<T>(f, drho, rho, ux, uy, om);

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run_strips_one_gpu(nx, ny, world, Re, steps, dtype, split_regions, two_step=True):
+def _run_strips_one_gpu(nx, ny, world, Re, steps, dtype, split_regions, two_step=True, tuning=None):
     import torch
     import latticeboltzmannsimulations_b200 as L
     from latticeboltzmannsimulations_b200 import _capi
@@ -25,7 +25,8 @@ def _run_strips_one_gpu(nx, ny, world, Re, steps, dtype, split_regions, two_step
     for (y0, nyl) in parts:
         nbytes = L.CavitySolver.state_bytes(nx, ny, 1, dtype, ny_local=nyl)
         raw = [torch.zeros(nbytes // tdt.itemsize, dtype=tdt, device="cuda") for _ in range(2)]
-        s = L.CavitySolver(nx, ny, 1, dtype, "MRT", y0=y0, ny_local=nyl, ext_buffers=[t.data_ptr() for t in raw])
+        s = L.CavitySolver(nx, ny, 1, dtype, "MRT", y0=y0, ny_local=nyl, ext_buffers=[t.data_ptr() for t in raw],
+                           tuning=tuning)
         s.set_reynolds(Re)
         s.init_equilibrium()
         solvers.append(s)
@@ -77,19 +78,23 @@ def test_strips_equal_single_domain_bitwise(nx, ny, world, split, dtype):
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("tuning", [None, {"slide_min_nodes": 0}, {"slide_min_nodes": 0, "slide_h": 14},
+                                    {"slide_min_nodes": 0, "slide_h": 50}])
 @pytest.mark.parametrize("nx,ny,world,split,steps", [(1100, 640, 2, True, 9), (900, 700, 3, True, 12), (1500, 410, 4, False, 7),
                                                       (800, 800, 5, True, 10)])
-def test_two_step_kernel_on_strips_bitwise(nx, ny, world, split, steps, dtype):
-    """Temporal blocking on y-strips (cavities above the size threshold of the two-step kernel): edge / interior
-    bands of whole tile rows, nine-row halo exchange, odd step counts -- bit-identical to the undecomposed run and
-    to the one-step kernels."""
+def test_two_step_kernel_on_strips_bitwise(nx, ny, world, split, steps, dtype, tuning):
+    """Temporal blocking on y-strips (shared-memory tiles by default at these sizes, the sliding-window kernel with
+    several segment heights through the tuning knob): edge / interior bands of whole tile rows / segments, nine-row
+    halo exchange, odd step counts -- bit-identical to the undecomposed run and to the one-step kernels."""
     import latticeboltzmannsimulations_b200 as L
     want = L.run_cavity(nx, ny, 1000, steps=steps, dtype=dtype, return_f=True)
-    got = _run_strips_one_gpu(nx, ny, world, 1000, steps, dtype, split)
-    if dtype == "float64" or nx >= 1024:                  # (fp32 takes it for wide cavities only)
+    got = _run_strips_one_gpu(nx, ny, world, 1000, steps, dtype, split, tuning=tuning)
+    if dtype == "float64" or tuning is not None:           # (fp32 takes no tiles; the sliding kernel serves both)
         assert got[3] >= (steps - 1) // 2                  # the two-step kernel really ran
     for a, b in zip(got[:3], want):
         assert np.array_equal(a, b)
+    if tuning is not None:
+        return
     one = _run_strips_one_gpu(nx, ny, world, 1000, steps, dtype, split, two_step=False)
     assert one[3] == 0
     for a, b in zip(one[:3], want):
