@@ -372,7 +372,8 @@ static int two_step_kind(const lbm_solver* s) {
     const long long nodes = (long long)s->cfg.nx * s->cfg.ny * s->cfg.batch;
     if (nodes < s->fused2_min_nodes) return TWO_NONE;
     const bool whole = s->nyl == s->cfg.ny;
-    if (s->use_slide && nodes >= s->slide_min_nodes && !s->cfg.turb) return TWO_SLIDE;
+    // the closure's per-node state has no halo exchange: two-step with turb = 1 on whole cavities only
+    if (s->use_slide && nodes >= s->slide_min_nodes && (!s->cfg.turb || whole)) return TWO_SLIDE;
     // the closure's per-node state has no halo exchange: two-step with turb = 1 on whole cavities only
     if (s->use_march && nodes >= s->march_min_nodes && (!s->cfg.turb || whole)) return TWO_MARCH;
     // shared-memory tiles: no closure, no frozen cavities
@@ -497,7 +498,7 @@ static int launch_fused2_rows(lbm_solver* s, int row_begin, int row_count, bool 
         a.seg_h = slide_seg_h(s);
         Slide2Launch L{};
         L.coll = s->cfg.collision == LBM_SRT ? COLL_SRT : s->cfg.collision == LBM_TRT ? COLL_TRT : COLL_MRT;
-        L.macros = macros; L.batch = s->cfg.batch; L.pdl = s->use_pdl != 0; L.st = st;
+        L.turb = s->cfg.turb != 0; L.macros = macros; L.batch = s->cfg.batch; L.pdl = s->use_pdl != 0; L.st = st;
         e = s->esz == 8 ? launch_slide2_f64(a, L) : launch_slide2_f32(a, L);
         if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("sliding two-step launch: ") + cudaGetErrorString(e));
         s->launches++;

@@ -24,7 +24,7 @@ cudaError_t launch_march2_f32(const StepArgs& a, const March2Launch& L);
 // Sliding-window two-step kernel (lbm_slide2.cuh), compiled per dtype in lbm_slide2_f64.cu / lbm_slide2_f32.cu.
 struct Slide2Launch {
     int coll;            // COLL_*
-    bool macros;
+    bool turb, macros;
     int batch;
     bool pdl;
     cudaStream_t st;

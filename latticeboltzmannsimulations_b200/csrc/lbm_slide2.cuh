@@ -24,7 +24,7 @@
 
 namespace lbm {
 
-template <typename T> struct SlideCfg {
+template <typename T, bool TURB = false> struct SlideCfg {
     static constexpr int TX = 512 / (int)sizeof(T);       // output columns of a strip: 64 fp64 / 128 fp32
     static constexpr int A = 16 / (int)sizeof(T);         // elements per 16-byte chunk: 2 / 4
     static constexpr int R = 4;                           // rows per iteration
@@ -37,7 +37,8 @@ template <typename T> struct SlideCfg {
     static constexpr int ITEMS = R * 64;                  // main items per sub-step: R rows x 64 (pairs of) columns
     static constexpr int NT = 288;                        // threads: 9 warps >= ITEMS + 2 R ring nodes = 264
     static constexpr int STAGE = 9 * R * SW;              // elements per staging buffer
-    static constexpr int WINDOW = 9 * WR * WW;
+    static constexpr int NPL = TURB ? 11 : 9;             // window planes: populations (+ Smagorinsky pi, rho of state t+1)
+    static constexpr int WINDOW = NPL * WR * WW;
     static constexpr int SIDE = TX + 2 + 4;               // lid density after sub-step 1 [TX + 2], corner carries [4]
     static constexpr int COPIERS = 9 * R;                 // one bulk copy per (population, row) of a stage
     static constexpr size_t DATA = (size_t)(2 * STAGE + WINDOW + SIDE) * sizeof(T);
@@ -105,9 +106,9 @@ template <> struct SlideItem<float> {
     static __device__ __forceinline__ float get(AT v, int i) { return i ? v.v.y : v.v.x; }
 };
 
-template <typename T, int COLL, bool MACROS, int MINB>
+template <typename T, int COLL, bool MACROS, int MINB, bool TURB>
 __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const StepArgs a) {
-    using Cfg = SlideCfg<T>;
+    using Cfg = SlideCfg<T, TURB>;
     constexpr int TX = Cfg::TX, A = Cfg::A, R = Cfg::R, SW = Cfg::SW, WW = Cfg::WW, WR = Cfg::WR, NT = Cfg::NT;
     constexpr int NV = Cfg::NV, WOFF = Cfg::WOFF;
     constexpr int E = (int)sizeof(T);
@@ -137,6 +138,11 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
     const T* carry_in = static_cast<const T*>(a.carry) + b * 4;
     const T* rl_in = static_cast<const T*>(a.rho_lid) + (long long)b * a.pitch;
     const unsigned stg_sa = slide_sa(stg);
+    // Smagorinsky state (whole cavities only): read side t-1, written side t+1
+    const T* pi_in = TURB ? static_cast<const T*>(a.pi_eq) + (long long)b * a.mplane : nullptr;
+    const T* rp_in = TURB ? static_cast<const T*>(a.rho_prev) + (long long)b * a.mplane : nullptr;
+    T* pi_out = TURB ? static_cast<T*>(a.pi_eq_out) + (long long)b * a.mplane : nullptr;
+    T* rp_out = TURB ? static_cast<T*>(a.rho_prev_out) + (long long)b * a.mplane : nullptr;
     // strip without wall columns whose staged halo chunks lie inside the row
     const bool xin = x0 >= A && x0 + TX + A <= a.nx;
 
@@ -217,7 +223,16 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
         if (left || right || lid || bot)
             slide_walls<T>(f, left, right, lid, bot, lid ? rl_in[x] : (T)1, rt.uLB, carry_in, c1);
         T rho, ux, uy;
-        node_update<T, COLL, false>(f, rt, left, right, lid, bot, rho, ux, uy);
+        if (TURB) {
+            const long long m = (long long)q * pitch + x;
+            T pi1;
+            const T om = smagorinsky_omega<T>(f, pi_in[m], rp_in[m], rt.tau0);
+            node_update<T, COLL, false, true>(f, rt, left, right, lid, bot, rho, ux, uy, om, &pi1);
+            w[9 * WR * WW] = pi1;
+            w[10 * WR * WW] = rho;
+        } else {
+            node_update<T, COLL, false>(f, rt, left, right, lid, bot, rho, ux, uy);
+        }
         if (lid) rl1[lx] = rho;
 #pragma unroll
         for (int k = 0; k < 9; ++k) w[k * WR * WW] = f[k];
@@ -241,7 +256,16 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
         if (left || right || lid || bot)
             slide_walls<T>(f, left, right, lid, bot, lid ? rl1[tx + 1] : (T)1, rt.uLB, c1, static_cast<T*>(a.carry_out) + b * 4);
         T rho, ux, uy;
-        node_update<T, COLL, MACROS>(f, rt, left, right, lid, bot, rho, ux, uy);
+        if (TURB) {
+            T pi2;
+            const T om = smagorinsky_omega<T>(f, pc[9 * WR * WW], pc[10 * WR * WW], rt.tau0);
+            node_update<T, COLL, MACROS, true>(f, rt, left, right, lid, bot, rho, ux, uy, om, &pi2);
+            const long long mt = (long long)yl * pitch + x;
+            pi_out[mt] = pi2;
+            rp_out[mt] = rho;
+        } else {
+            node_update<T, COLL, MACROS>(f, rt, left, right, lid, bot, rho, ux, uy);
+        }
         if (lid) static_cast<T*>(a.rho_lid_out)[(long long)b * a.pitch + x] = rho;
         T* d = dst + (long long)(yl + 1) * pitch + x;
 #pragma unroll
@@ -272,6 +296,12 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
         ws = ws >= WR ? ws - WR : ws;
         T* w = win + ws * WW + ilx + WOFF;
         if (main_item && inner1) {
+            AT pi0, rp0;
+            if (TURB) {                                            // state t-1 of this item's nodes
+                const long long m = (long long)(s + ij) * pitch + (x0 + itx);
+                pi0 = Item::ld(pi_in + m);
+                rp0 = Item::ld(rp_in + m);
+            }
             const T* c = S + ij * SW + ilx + (A - 1);              // first node of the item in population 0's staged rows
             AT f[9];
             f[0] = Item::ld(c);
@@ -283,11 +313,20 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
             f[6] = Item::ldx(c + 6 * R * SW, 1);
             f[7] = Item::ldx(c + 7 * R * SW, 1);
             f[8] = Item::ldx(c + 8 * R * SW, -1);
-            AT rho, ux, uy;
-            node_update<AT, COLL, false>(f, rta, false, false, false, false, rho, ux, uy);
+            AT rho, ux, uy, pi1;
+            if (TURB) {
+                const AT om = smagorinsky_omega<AT>(f, pi0, rp0, rta.tau0);
+                node_update<AT, COLL, false, true>(f, rta, false, false, false, false, rho, ux, uy, om, &pi1);
+            } else {
+                node_update<AT, COLL, false>(f, rta, false, false, false, false, rho, ux, uy);
+            }
             slide_mbar_wait(bar_free, it & 1);                     // everybody's sub-step 2 of the previous iteration has
 #pragma unroll                                                     // read the window rows overwritten now
             for (int k = 0; k < 9; ++k) Item::st(w + k * WR * WW, f[k]);
+            if (TURB) {
+                Item::st(w + 9 * WR * WW, pi1);
+                Item::st(w + 10 * WR * WW, rho);
+            }
         } else {
             slide_mbar_wait(bar_free, it & 1);
             if (main_item) {
@@ -325,8 +364,17 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
                 f[7] = Item::ldx(pu + 7 * WR * WW, 1);
                 f[8] = Item::ldx(pu + 8 * WR * WW, -1);
                 AT rho, ux, uy;
-                node_update<AT, COLL, MACROS>(f, rta, false, false, false, false, rho, ux, uy);
                 const int yl = s - 1 + ij;
+                if (TURB) {
+                    AT pi2;
+                    const AT om = smagorinsky_omega<AT>(f, Item::ld(pc + 9 * WR * WW), Item::ld(pc + 10 * WR * WW), rta.tau0);
+                    node_update<AT, COLL, MACROS, true>(f, rta, false, false, false, false, rho, ux, uy, om, &pi2);
+                    const long long mt = (long long)yl * pitch + (x0 + itx);
+                    Item::st(pi_out + mt, pi2);
+                    Item::st(rp_out + mt, rho);
+                } else {
+                    node_update<AT, COLL, MACROS>(f, rta, false, false, false, false, rho, ux, uy);
+                }
                 T* d = dst + (long long)(yl + 1) * pitch + (x0 + itx);
 #pragma unroll
                 for (int k = 0; k < 9; ++k) Item::st(d + k * P, f[k]);

@@ -6,10 +6,10 @@
 namespace lbm {
 namespace {
 
-template <typename T, int COLL, bool MACROS, int MINB>
+template <typename T, int COLL, bool MACROS, int MINB, bool TURB>
 cudaError_t slide_launch_cfg(const StepArgs& a, const Slide2Launch& L) {
-    using Cfg = SlideCfg<T>;
-    auto kern = lbm_step_slide2<T, COLL, MACROS, MINB>;
+    using Cfg = SlideCfg<T, TURB>;
+    auto kern = lbm_step_slide2<T, COLL, MACROS, MINB, TURB>;
     static bool attr_done[64] = {};                // cudaFuncSetAttribute is per device
     int dev = 0;
     if (cudaError_t e = cudaGetDevice(&dev)) return e;
@@ -33,8 +33,12 @@ cudaError_t slide_launch_cfg(const StepArgs& a, const Slide2Launch& L) {
 
 template <typename T, int COLL, int MINB>
 cudaError_t slide_launch_flags(const StepArgs& a, const Slide2Launch& L) {
-    if (L.macros) return slide_launch_cfg<T, COLL, true, MINB>(a, L);
-    return slide_launch_cfg<T, COLL, false, MINB>(a, L);
+    if (L.turb) {
+        if (L.macros) return slide_launch_cfg<T, COLL, true, MINB, true>(a, L);
+        return slide_launch_cfg<T, COLL, false, MINB, true>(a, L);
+    }
+    if (L.macros) return slide_launch_cfg<T, COLL, true, MINB, false>(a, L);
+    return slide_launch_cfg<T, COLL, false, MINB, false>(a, L);
 }
 
 template <typename T, int MINB>

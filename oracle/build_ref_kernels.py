@@ -53,7 +53,8 @@ extern "C" int ref_run(int coll, int nx, int ny, const float* params, int nparam
         else funRT_MRT<<<grid, block>>>(d_fin, d_ftemp, d_feq, d_rho, d_u, d_taus);
         funBC<<<grid, block>>>(d_ftemp, d_feq, d_fin);
     }
-    cudaError_t e = cudaDeviceSynchronize();
+    cudaError_t e = cudaGetLastError();                             /* a failed launch (resources) is not a sync error */
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaMemcpy(fin, d_fin, 9 * n * 4, cudaMemcpyDeviceToHost);     /* the scripts download ftemp_g == fin_g, :755 */
     cudaMemcpy(rho, d_rho, n * 4, cudaMemcpyDeviceToHost);
     cudaMemcpy(u, d_u, 2 * n * 4, cudaMemcpyDeviceToHost);
@@ -98,9 +99,11 @@ def build(force: bool = False) -> str:
             cu = os.path.join(tmp, "ref_kernels.cu")
             with open(cu, "w") as fh:
                 fh.write(generate_source(real))
-            # -fmad=false for the fp64 build: no contraction, i.e. the arithmetic the source text spells out
+            # fp64 build: -fmad=false (no contraction: the arithmetic the source text spells out) and 64 registers per
+            # thread, without which the reference's 32 x 32 = 1024-thread blocks (MRT_GPU.py:53-54) cannot launch
             subprocess.check_call([NVCC, "-O2", "-w", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
-                                   "-shared"] + (["-fmad=false"] if real == "double" else []) + ["-o", out, cu])
+                                   "-shared"] + (["-fmad=false", "-maxrregcount=64"] if real == "double" else []) +
+                                  ["-o", out, cu])
     return OUT
 
 

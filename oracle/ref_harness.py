@@ -122,10 +122,11 @@ def load_ref_functions(variant: str = "functions"):
 # The reference's own CUDA kernels (built by oracle/build_ref_kernels.py), run on the GPU box
 # --------------------------------------------------------------------------------------------
 REF_KERNELS_SO = os.path.join(REF_BUILD_DIR, "libref_kernels.so")
+REF_KERNELS_F64_SO = os.path.join(REF_BUILD_DIR, "libref_kernels_f64.so")     # same text, float -> double
 
 
-def ref_kernels_built() -> bool:
-    return os.path.exists(REF_KERNELS_SO)
+def ref_kernels_built(dtype: str = "float32") -> bool:
+    return os.path.exists(REF_KERNELS_SO if dtype == "float32" else REF_KERNELS_F64_SO)
 
 
 def run_reference_kernels(nx: int, ny: int, Re: float, steps: int, collision: str = "MRT", turb: int = 0,

@@ -5,13 +5,15 @@ import numpy as np
 sys.path.insert(0, ".")
 import latticeboltzmannsimulations_b200 as L
 from oracle import lbm_oracle as O, ref_harness as R
-for (nx, ny, Re, steps) in ((64, 64, 100.0, 60), (96, 64, 1000.0, 120)):
+for dtype in ("float32", "float64"):
+  print("reference kernels compiled as", dtype)
+  for (nx, ny, Re, steps) in ((64, 64, 100.0, 60), (96, 64, 1000.0, 120), (128, 96, 3200.0, 400)):
     for coll in ("MRT", "SRT", "TRT"):
         for turb in (0, 1):
-            ref = R.run_reference_kernels(nx, ny, Re, steps, coll, turb)
+            ref = R.run_reference_kernels(nx, ny, Re, steps, coll, turb, dtype=dtype)
             p = O.Params(nx, ny, Re=Re, collision=coll, turb=turb)
             want = O.run(p, steps, form="push")
-            got = L.run_cavity(nx, ny, Re, steps=steps, collision=coll, dtype="float32", turb=bool(turb), return_f=True)
+            got = L.run_cavity(nx, ny, Re, steps=steps, collision=coll, dtype=dtype, turb=bool(turb), return_f=True)
             eo = [float(np.abs(a - b).max()) for a, b in zip(ref, want)]
             ep = [float(np.abs(a - b).max()) for a, b in zip(ref, got)]
             print("%dx%d Re=%g N=%d %s turb=%d: ref-vs-oracle rho %.2e u %.2e f %.2e | ref-vs-product rho %.2e u %.2e f %.2e" % (
