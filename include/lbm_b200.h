@@ -167,6 +167,14 @@ int lbm_mean_u(lbm_handle_t h, double* mean_out, void* stream);
  * cavities keep their populations and macros and no longer cost bandwidth; they cannot be re-activated. */
 int lbm_set_active(lbm_handle_t h, const int32_t* active, void* stream);
 
+/* The whole stopping rule of MRT_GPU_datagen.py:726-733 on the device, for every cavity of the batch at once: reduce
+ * mean(u) of the stored velocity field, compare with the value of the previous call (zeros before the first, :223),
+ * abs(mean - past) / uLB < tol increments the cavity's counter (never reset, as in the reference), a counter above
+ * hits - 1 retires the cavity exactly like lbm_set_active would (`break`, :731-733).  No host round trip is needed
+ * between checks; with active_out != NULL ([batch] on the host) the per-cavity flags are read back (one small copy +
+ * stream synchronisation) so that the caller can stop when all are 0.  Whole-cavity handles, after at least one step. */
+int lbm_converge_check(lbm_handle_t h, double tol, int hits, int32_t* active_out, void* stream);
+
 /* Diagnostics of the stored (lagged) velocity field of one cavity, computed on the device instead of downloading the
  * full fields as the scripts do every Pinterval (MRT_GPU.py:764-776, 793-800 / MRT.py:504-516):
  *   ux_col    [ny_local]  u_x on the middle column x = nx/2                       (may be NULL)

@@ -26,7 +26,7 @@ SYMBOLS = [
     "lbm_last_error", "lbm_abi_version", "lbm_device_count", "lbm_state_bytes", "lbm_create", "lbm_destroy",
     "lbm_get_layout", "lbm_set_tuning", "lbm_set_reynolds", "lbm_set_rates", "lbm_init_equilibrium", "lbm_upload_f",
     "lbm_download_f", "lbm_step", "lbm_step_region", "lbm_swap", "lbm_step2_region", "lbm_swap2", "lbm_step2_available", "lbm_buffer_ptr", "lbm_get_macros",
-    "lbm_get_macros_current", "lbm_equilibrium", "lbm_mean_u", "lbm_set_active", "lbm_diagnostics", "lbm_sync", "lbm_get_counters", "lbm_engine_name",
+    "lbm_get_macros_current", "lbm_equilibrium", "lbm_mean_u", "lbm_set_active", "lbm_converge_check", "lbm_diagnostics", "lbm_sync", "lbm_get_counters", "lbm_engine_name",
 ]
 
 
@@ -94,6 +94,7 @@ def load():
                                     C.c_void_p]
     lib.lbm_mean_u.argtypes = [H, C.POINTER(C.c_double), C.c_void_p]
     lib.lbm_set_active.argtypes = [H, C.POINTER(C.c_int32), C.c_void_p]
+    lib.lbm_converge_check.argtypes = [H, C.c_double, C.c_int, C.POINTER(C.c_int32), C.c_void_p]
     lib.lbm_diagnostics.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
     lib.lbm_sync.argtypes = [H]
     lib.lbm_get_counters.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]

@@ -91,6 +91,8 @@ struct lbm_solver {
     int* active = nullptr;     // device copy of the per-cavity active flags (NULL until lbm_set_active is used)
     std::vector<int> active_host;
     double* usum = nullptr;    // [batch] accumulator of lbm_mean_u
+    double* conv_past = nullptr;   // [batch] mean(u) at the previous convergence check (device)
+    int* conv_count = nullptr;     // [batch] hits so far; [batch .. 2 batch) cavities retired by the last check
     CavityParams* cav = nullptr;
     std::vector<CavityParams> cav_host;
     bool cav_dirty = true;
@@ -128,6 +130,7 @@ struct lbm_solver {
 
 // A fresh state (init / upload) un-freezes every cavity; graphs captured with the old flag pointer are dropped.
 static void reset_active(lbm_solver* s) {
+    if (s->conv_past) { cudaFree(s->conv_past); s->conv_past = nullptr; cudaFree(s->conv_count); s->conv_count = nullptr; }
     if (!s->active) return;
     cudaFree(s->active);
     s->active = nullptr;
@@ -669,7 +672,7 @@ int lbm_destroy(lbm_handle_t s) {
     cudaFree(s->rho); cudaFree(s->ux); cudaFree(s->uy);
     cudaFree(s->rho_lid); cudaFree(s->carry); cudaFree(s->cav);
     cudaFree(s->pi_eq); cudaFree(s->rho_prev);
-    cudaFree(s->active); cudaFree(s->usum);
+    cudaFree(s->active); cudaFree(s->usum); cudaFree(s->conv_past); cudaFree(s->conv_count);
     cudaFree(s->staging); cudaFree(s->scratch);
     for (int i = 0; i < 4; ++i) if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
     if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
@@ -1317,6 +1320,62 @@ int lbm_set_active(lbm_handle_t s, const int32_t* active, void* stream) {
     }
     CK(cudaMemcpyAsync(s->active, s->active_host.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
+    return LBM_OK;
+}
+
+int lbm_converge_check(lbm_handle_t s, double tol, int hits, int32_t* active_out, void* stream) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    if (!(tol > 0.0) || hits < 1) return fail(LBM_EINVAL, "tol must be positive and hits >= 1");
+    if (s->pre) return fail(LBM_ESTATE, "the convergence check needs at least one step (stored velocity field)");
+    if (s->nyl != s->cfg.ny) return fail(LBM_ESTATE, "the convergence check needs whole cavities");
+    int rc = set_device(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = sync_params(s, st);
+    if (rc) return rc;
+    const int nb = s->cfg.batch;
+    if (!s->active) {       // first use: every cavity active (kernel arguments change: drop captured graphs)
+        CK(cudaMalloc(&s->active, sizeof(int) * nb));
+        s->active_host.assign(nb, 1);
+        CK(cudaMemcpyAsync(s->active, s->active_host.data(), sizeof(int) * nb, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        drop_graphs(s);
+    }
+    if (!s->conv_past) {    // u_past = zeros, count = 0 (MRT_GPU_datagen.py:223, 705)
+        CK(cudaMalloc(&s->conv_past, sizeof(double) * nb));
+        CK(cudaMalloc(&s->conv_count, sizeof(int) * 2 * nb));
+        CK(cudaMemsetAsync(s->conv_past, 0, sizeof(double) * nb, st));
+        CK(cudaMemsetAsync(s->conv_count, 0, sizeof(int) * 2 * nb, st));
+    }
+    if (!s->usum) CK(cudaMalloc(&s->usum, sizeof(double) * nb));
+    CK(cudaMemsetAsync(s->usum, 0, sizeof(double) * nb, st));
+    dim3 grid(148 * 2, nb);
+    if (s->esz == 8) lbm_sum_u<double><<<grid, 256, 0, st>>>((const double*)s->ux, (const double*)s->uy, s->usum, s->cfg.nx, s->nyl, s->pitch, s->mplane);
+    else lbm_sum_u<float><<<grid, 256, 0, st>>>((const float*)s->ux, (const float*)s->uy, s->usum, s->cfg.nx, s->nyl, s->pitch, s->mplane);
+    int* newly = s->conv_count + nb;
+    lbm_converge_rule<<<(nb + 127) / 128, 128, 0, st>>>(s->usum, 2.0 * (double)s->cfg.nx * (double)s->nyl, s->cav, s->conv_past,
+                                                       s->conv_count, s->active, newly, tol, hits, nb);
+    // retired cavities: both A/B buffers and both halves of the side arrays must hold their final state
+    const size_t cav_bytes = (size_t)s->cavity * s->esz;
+    const size_t rl_bytes = (size_t)s->pitch * s->esz, rl_half = (size_t)nb * rl_bytes;
+    const size_t ca_bytes = 4 * (size_t)s->esz, ca_half = (size_t)nb * ca_bytes;
+    const size_t m_bytes = (size_t)s->mplane * s->esz, m_half = (size_t)nb * m_bytes;
+    const int o = s->side ^ 1;
+    dim3 cg(64, nb);
+    lbm_freeze_copy<<<cg, 256, 0, st>>>(newly, (const char*)s->f[s->cur], (char*)s->f[s->cur ^ 1], cav_bytes);
+    lbm_freeze_copy<<<dim3(1, nb), 256, 0, st>>>(newly, (const char*)s->rho_lid + s->side * rl_half, (char*)s->rho_lid + o * rl_half, rl_bytes);
+    lbm_freeze_copy<<<dim3(1, nb), 32, 0, st>>>(newly, (const char*)s->carry + s->side * ca_half, (char*)s->carry + o * ca_half, ca_bytes);
+    if (s->pi_eq) {
+        lbm_freeze_copy<<<cg, 256, 0, st>>>(newly, (const char*)s->pi_eq + s->side * m_half, (char*)s->pi_eq + o * m_half, m_bytes);
+        lbm_freeze_copy<<<cg, 256, 0, st>>>(newly, (const char*)s->rho_prev + s->side * m_half, (char*)s->rho_prev + o * m_half, m_bytes);
+    }
+    s->launches += s->pi_eq ? 7 : 5;
+    CK(cudaGetLastError());
+    if (active_out) {
+        CK(cudaMemcpyAsync(s->active_host.data(), s->active, sizeof(int) * nb, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int b = 0; b < nb; ++b) active_out[b] = s->active_host[b];
+    }
     return LBM_OK;
 }
 

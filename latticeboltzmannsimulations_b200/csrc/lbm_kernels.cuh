@@ -514,6 +514,37 @@ __global__ void lbm_sum_u(const T* __restrict__ ux, const T* __restrict__ uy, do
     }
 }
 
+// The stopping rule of MRT_GPU_datagen.py:726-733 for every cavity of a batch, on the device: one thread per cavity
+// compares the mean of the stored velocity field with the one of the previous check, counts the hits (never reset, as
+// in the reference) and retires the cavity when the count exceeds hits - 1.  newly[b] = 1 marks cavities retired by
+// this call (their buffers are equalised by lbm_freeze_copy).
+__global__ void lbm_converge_rule(const double* __restrict__ usum, double denom, const CavityParams* __restrict__ cav,
+                                  double* __restrict__ past, int* __restrict__ count, int* __restrict__ active,
+                                  int* __restrict__ newly, double tol, int hits, int nb) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    newly[b] = 0;
+    if (!active[b]) return;
+    const double mean = usum[b] / denom;
+    if (fabs(mean - past[b]) / cav[b].uLB < tol) {
+        const int c = ++count[b];
+        if (c > hits - 1) { active[b] = 0; newly[b] = 1; }
+    }
+    past[b] = mean;
+}
+
+// Copy `n` bytes (a multiple of 16) per cavity from src to dst for the cavities flagged in newly[]: a retired cavity
+// must hold the same state in both A/B buffers and both halves of the side arrays.
+__global__ void lbm_freeze_copy(const int* __restrict__ newly, const char* __restrict__ src, char* __restrict__ dst,
+                                size_t bytes_per_cavity) {
+    const int b = blockIdx.y;
+    if (!newly[b]) return;
+    const uint4* s = reinterpret_cast<const uint4*>(src + (size_t)b * bytes_per_cavity);
+    uint4* d = reinterpret_cast<uint4*>(dst + (size_t)b * bytes_per_cavity);
+    const size_t n = bytes_per_cavity / 16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+
 // Diagnostics the reference scripts compute on the host after downloading the full fields (MRT_GPU.py:764-776,
 // 793-800): centre-lines ux(x = nx/2, :) and uy(:, y = ny/2), and the vortex-centre search = argmin of |u|^2 with a
 // border of BCoffset = nx/40 nodes (and optionally a box around the first centre) masked out.

@@ -292,4 +292,5 @@ def datagen_sharded(Re_list: Sequence[float], nx: int = 384, ny: int = 384, uLB:
         f_final[idx] = loc[0]
         u_final[idx] = loc[1]
         feq0 = loc[2] if feq0 is None else feq0
-    return f_final, u_final, feq0, np.asarray(list(Re_list), dtype=np.float64)
+    from .cavity import _re_range_array
+    return f_final, u_final, feq0, _re_range_array(Re_list)

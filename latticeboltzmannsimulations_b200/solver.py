@@ -218,6 +218,16 @@ class CavitySolver:
             raise ValueError("need one flag per cavity")
         _capi.check(self._lib.lbm_set_active(self._h, flags.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(stream)))
 
+    def converge_check(self, tol: float = 1e-7, hits: int = 6, read_back: bool = True, stream: int = 0):
+        """One evaluation of the reference's stopping rule for every cavity, on the device (``lbm_converge_check``);
+        returns the per-cavity active flags (``None`` with ``read_back=False``: no host synchronisation at all)."""
+        if not read_back:
+            _capi.check(self._lib.lbm_converge_check(self._h, float(tol), int(hits), None, C.c_void_p(stream)))
+            return None
+        out = (C.c_int32 * self.batch)()
+        _capi.check(self._lib.lbm_converge_check(self._h, float(tol), int(hits), out, C.c_void_p(stream)))
+        return np.array(out[:], dtype=np.int32)
+
     def diagnostics(self, cavity: int = 0, vortices: bool = True, stream: int = 0):
         """Centre-lines and vortex centres of the stored velocity field, reduced on the device.
 

@@ -78,3 +78,23 @@ def test_functions_shim_signature_errors():
         functions.set_omega(0.08, 100.5, 64)
     functions.set_omega(0.08, 100.0, 64)
     assert abs(functions.omega - 2.0 / (6 * 0.08 * 64 / 100 + 1)) < 1e-16
+
+
+def test_dataset_writer_names_and_dtypes(tmp_path):
+    """save_dataset writes the four files of MRT_GPU_datagen.py:899-902; Re_range is int64 when integral (np.arange)."""
+    from latticeboltzmannsimulations_b200.cavity import save_dataset, _re_range_array
+    f = np.zeros((2, 9, 8, 6), np.float32); u = np.zeros((2, 2, 8, 6), np.float32); feq = np.ones((9, 8, 6), np.float32)
+    save_dataset(str(tmp_path), f, u, feq, [100.0, 110.0])
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["Re_range.npy", "f_final.npy", "feq_initial.npy", "u_final.npy"]
+    assert np.load(tmp_path / "Re_range.npy").dtype == np.int64
+    assert _re_range_array([100.5, 200.0]).dtype == np.float64 and _re_range_array(np.arange(3)).dtype == np.int64
+    assert np.load(tmp_path / "f_final.npy").shape == (2, 9, 8, 6)
+
+
+def test_batch_limit_is_validated():
+    from latticeboltzmannsimulations_b200 import _capi
+    lib = _capi.load()
+    cfg = _capi.Config(nx=8, ny=8, batch=70000, dtype=1, collision=2, turb=0, y0=0, ny_local=0, device=-1, engine=0,
+                       semantics=0, reserved=0)
+    out = ctypes.c_size_t()
+    assert lib.lbm_state_bytes(ctypes.byref(cfg), ctypes.byref(out)) == _capi.LBM_EINVAL

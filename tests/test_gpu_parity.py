@@ -319,6 +319,63 @@ def test_datagen_convergence_rule_matches_reference_loop():
         assert np.abs(f_final[b] - fin).max() <= 1e-12 and np.abs(u_final[b] - u).max() / 0.08 <= 1e-12
 
 
+def test_datagen_without_convergence_returns_the_last_check_and_writes_the_dataset(tmp_path):
+    """A cavity that never meets the rule returns -- like the script, which only downloads at checks and saves what it
+    downloaded last (MRT_GPU_datagen.py:725-726, 899-902) -- the fields of its last check; out_dir gets the four files
+    under the names, shapes and dtypes the CNN scripts load (CNN_test.py:18-21, CNNTen_384/CNN_Ten.py:22-27)."""
+    import latticeboltzmannsimulations_b200 as L
+    nx, ny, P, maxIt = 32, 24, 50, 180
+    Re_list = np.arange(100, 130, 10)                      # int64, like np.arange(100, 5100, 10) of the reference
+    f_final, u_final, feq0, Re_out, steps = L.datagen(Re_list, nx, ny, collision="SRT", dtype="float32", turb=True,
+                                                      converge=True, Pinterval=P, tol=1e-12, maxIt=maxIt, return_steps=True,
+                                                      out_dir=str(tmp_path))
+    assert list(steps) == [151, 151, 151]                  # checks at It = 0, 50, 100, 150; It = 150 is the last one
+    for b, Re in enumerate(Re_list):
+        rho, u, f = L.run_cavity(nx, ny, float(Re), steps=151, collision="SRT", dtype="float32", turb=True, return_f=True)
+        assert np.array_equal(f, f_final[b]) and np.array_equal(u, u_final[b])
+    Re = np.load(tmp_path / "Re_range.npy"); feq = np.load(tmp_path / "feq_initial.npy")
+    fun = np.load(tmp_path / "f_final.npy"); vel = np.load(tmp_path / "u_final.npy")
+    assert Re.dtype == np.int64 and np.array_equal(Re, Re_list) and Re_out.dtype == np.int64
+    assert fun.shape == (3, 9, nx, ny) and vel.shape == (3, 2, nx, ny) and feq.shape == (9, nx, ny)
+    assert fun.dtype == vel.dtype == feq.dtype == np.float32
+    assert np.array_equal(fun, f_final) and np.array_equal(vel, u_final) and np.array_equal(feq, feq0)
+    velBC = vel.copy(); velBC[:, :, :, 1:] = 0             # CNN_Ten.py:26-27: the lid row is column 0 of the last axis
+    assert np.all(velBC[:, 0, :, 0] == np.float32(0.08))
+
+
+def test_frozen_cavity_survives_downloads_and_further_steps():
+    """lbm_download_f must not disturb a frozen cavity (it used to finalize into the buffer the cavity still needs after
+    the next parity flip): freeze, download, step on, download -- the frozen cavity is unchanged each time, the others
+    equal their standalone runs; freezing before the first step is refused."""
+    import latticeboltzmannsimulations_b200 as L
+    nx, ny, Re = 48, 36, [100.0, 400.0, 1000.0]
+    with L.CavitySolver(nx, ny, 3, "float64", "MRT") as s:
+        s.set_reynolds(Re)
+        s.init_equilibrium()
+        with pytest.raises(L.LBMError):
+            s.set_active([1, 0, 1])                        # pre-collision state: nothing to freeze yet
+        s.step(40)
+        s.set_active([1, 0, 1])
+        f0 = s.download_f()
+        for extra in (1, 2, 3, 10):
+            s.step(extra)
+            f = s.download_f()
+            f_again = s.download_f()
+            assert np.array_equal(f[1], f0[1]) and np.array_equal(f, f_again)
+        rho, u = s.macros()
+    for b, steps in ((0, 56), (1, 40), (2, 56)):
+        r0, u0, fb = L.run_cavity(nx, ny, Re[b], steps=steps, return_f=True)
+        assert np.array_equal(f[b], fb) and np.array_equal(u[b], u0), b
+
+
+def test_macros_rejects_non_contiguous_outputs():
+    import latticeboltzmannsimulations_b200 as L
+    with L.CavitySolver(32, 24) as s:
+        s.init_equilibrium(); s.step(3)
+        with pytest.raises(ValueError):
+            s.macros(rho_out=np.empty((24, 32)).T, u_out=np.empty((2, 32, 24)))
+
+
 def test_device_resident_io_with_torch_tensors():
     """Zero-copy path of the C ABI (on_device = 1): torch CUDA tensors in the reference layout go in and come out
     without touching the host, on a non-default stream, and give the same bits as the host-array path."""

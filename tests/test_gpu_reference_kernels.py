@@ -41,7 +41,8 @@ def test_oracle_and_product_against_reference_cuda_kernels(coll, turb, nx, ny, R
     assert max(e_prod) <= TOL, ("reference kernels vs product fp32", coll, turb, e_prod)
 
 
-TOL64 = 1e-12
+TOL64 = 1e-12            # product fp64 vs the reference kernels in double (measured <= 4.5e-14, profiles/r02_reference_kernels_check.txt)
+TOL64_ORACLE = 1e-15     # oracle vs the reference kernels in double: measured 0.0 -- the same bits -- in all 18 cases
 
 
 @pytest.mark.skipif(not R.ref_kernels_built("float64"), reason="oracle/_ref/libref_kernels_f64.so not built")
@@ -57,7 +58,7 @@ def test_fp64_pin_against_reference_cuda_kernels_in_double(coll, turb, nx, ny, R
     p = O.Params(nx, ny, Re=Re, collision=coll, turb=turb)
     want = O.run(p, steps, semantics="C", form="push")
     e_oracle = _err(ref, want)
-    assert max(e_oracle) <= TOL64, ("reference kernels (double) vs oracle", coll, turb, e_oracle)
+    assert max(e_oracle) <= TOL64_ORACLE, ("reference kernels (double) vs oracle", coll, turb, e_oracle)
     got = L.run_cavity(nx, ny, Re, steps=steps, collision=coll, dtype="float64", turb=bool(turb), return_f=True)
     e_prod = _err(ref, got)
     assert max(e_prod) <= TOL64, ("reference kernels (double) vs product fp64", coll, turb, e_prod)
