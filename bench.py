@@ -39,6 +39,8 @@ WORKLOADS = {
     "cavity384": (384, 384, 3200.0, "lid-driven cavity 384x384 Re=3200 uLB=0.08 D2Q9 MRT (BASELINE config 2)"),
     "datagen256": (384, 384, None, "batched sweep: 256 cavities 384x384, Re = linspace(100, 10000, 256), sharded "
                                    "cavity b -> rank b mod N, no communication (BASELINE config 4)"),
+    "refdefault640": (640, 640, 1000.0, "the reference's own published shape and default configuration: 640x640, SRT, "
+                                        "turb=1 (Smagorinsky), fp32, 3000 iterations (MRT_GPU.py:48-58, BASELINE.md section 1)"),
 }
 BYTES_PER_NODE = {"float64": 144, "float32": 72}
 
@@ -155,30 +157,47 @@ def cpu_baseline_sample(variant: str, Re: float, budget_s: float, n: int):
 
 # ----------------------------------------------------------------------------------------------------------------
 def run_reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the step (functions.allfunc of functions.pyx, compiled from the
+    reference sources into oracle/_ref) on this box's host cores.  `value` is the module AS SHIPPED: its OpenMP loops
+    carry a hard-coded num_threads=4 (functions.pyx:69), so four threads are all it can use; the same source with that
+    literal removed (every host thread) is reported beside it as `all_cores_value`.  Under torchrun the launcher puts
+    OMP_NUM_THREADS=1 into every rank's environment: the thread count is set explicitly here, before the OpenMP runtime
+    is loaded with the module."""
     if rank != 0:
         return
+    ncpu = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
     wl = args.workload or ("cavity4096" if args.gpus == 1 else "cavity32768")
     nx, ny, Re, desc = WORKLOADS[wl]
     Re = Re or 5000.0
-    kind, cores, run = cpu_step_timer("functions_allcores")
-    # bounded sample: choose the sub-cavity so that warmup + steps calls fit in ~100 s
-    probe_n = 512
-    t_probe = run(probe_n, Re, 2) / 2
-    per_node = t_probe / (probe_n * probe_n)
-    total_calls = args.steps + args.warmup
-    n = int((100.0 / max(total_calls, 1) / per_node) ** 0.5) // 32 * 32
-    n = max(64, min(n, nx, 2048))
+    kind, cores, run = cpu_step_timer("functions")
+    # the whole grid when it fits the host and the time budget (4096^2: ~1.3 s per step), else a bounded sub-cavity
+    n = min(nx, 4096)
     run(n, Re, max(args.warmup - 1, 0))                       # warm-up calls (run() itself adds one)
     t = run(n, Re, args.steps)
     mlups = n * n * args.steps / t / 1e6
-    cb = {"value": round(mlups, 2), "unit": "MLUPS", "cores": cores, "kind": kind,
-          "sample": "each step = one functions.allfunc call (reference Cython/OpenMP step, SRT fp64, all %d host "
-                    "threads) on a %dx%d sub-cavity of the workload" % (cores, n, n)}
+    extra = {}
+    try:
+        kind_a, cores_a, run_a = cpu_step_timer("functions_allcores")
+        steps_a = max(3, args.steps // 2)
+        ta = run_a(n, Re, steps_a)
+        extra = {"all_cores_value": round(n * n * steps_a / ta / 1e6, 2), "all_cores": cores_a,
+                 "all_cores_note": "same source with the num_threads=4 literal removed (modified thread count), %d steps" % steps_a}
+    except Exception as exc:      # pragma: no cover
+        extra = {"all_cores_error": str(exc)}
+    sample = ("each step = one functions.allfunc call (reference Cython/OpenMP step as shipped: SRT, fp64, num_threads=4 "
+              "hard-coded at functions.pyx:69) on %s; the CPU path has no MRT collision and no Smagorinsky closure, "
+              "the wall rule differs (SURVEY.md 3.4)" % ("the full %dx%d grid of the workload" % (n, n) if n == nx else
+                                                          "a %dx%d sub-cavity of the %dx%d workload" % (n, n, nx, ny)))
+    cb = {"value": round(mlups, 2), "unit": "MLUPS", "cores": cores, "kind": kind, "sample": sample}
+    cb.update(extra)
     out = {"impl": "reference", "metric": "MLUPS", "value": round(mlups, 2), "unit": "MLUPS", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t / args.steps * 1e3, 4),
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": wl, "description": desc, "sample_grid": [n, n]},
+           "config": {"workload": wl, "description": desc, "sample_grid": [n, n], "collision": "SRT (the only one the CPU path has)",
+                      "host_logical_cpus": ncpu, "omp_num_threads_env": os.environ["OMP_NUM_THREADS"]},
            "cpu_baseline": cb,
            "e2e": {"value": round(mlups, 2), "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -237,11 +256,11 @@ def run_single_gpu(args):
         results[dtype] = timed_run(dtype, dtype == "float64")
     launches = results["float64"]["launches"]
     # the one-step kernels (temporal blocking off) for reference: these are the HBM-bound ones
-    os.environ["LBM_B200_FUSED2"] = "0"
+    os.environ["LBM_B200_TUNING"] = "two_step=0"
     try:
         one_step = {dt: timed_run(dt, False) for dt in ("float64", "float32")}
     finally:
-        del os.environ["LBM_B200_FUSED2"]
+        del os.environ["LBM_B200_TUNING"]
     # ---- e2e through the host API, fp64: pinned f0 upload + K steps + rho,u download -----------------------------
     huge = nx * ny * 72 > 8e9            # a 77 GB initial state cannot sensibly come from the host: init on device
     rho_out = torch.empty((nx, ny), dtype=torch.float64, pin_memory=True).numpy()
@@ -272,16 +291,56 @@ def run_single_gpu(args):
            "call": ("CavitySolver.init_equilibrium() + step(K) + macros() -> pinned rho,u (state too large for a host upload)"
                     if huge else "CavitySolver.upload_f(pinned f0) + step(K) + macros() -> pinned rho,u"),
            "seconds": round(e2e_s, 4)}
-    # ---- extra: config 2 (384^2, L2-resident, launch-latency-bound) ------------------------------------------------
+    # ---- extra: the other configurations, each timed like the headline (device-resident, CUDA events) ----------------
     extra = {}
+
+    def quick(nxx, nyy, dtype, coll, turb, steps, warm, key, tuning=None):
+        try:
+            with L.CavitySolver(nxx, nyy, 1, dtype, coll, turb, engine=args.engine, tuning=tuning) as s:
+                s.set_reynolds(WORKLOADS.get(key, (0, 0, 1000.0))[2] or 1000.0, 0.08)
+                s.init_equilibrium(); s.step(warm, write_macros=False, stream=stream)
+                ms = time_device_steps(lambda k: s.step(k, write_macros=False, stream=stream), torch.cuda.synchronize, steps, torch)
+                return round(nxx * nyy * steps / ms / 1e3, 1), round(ms / steps * 1e3, 3)
+        except Exception as exc:      # pragma: no cover
+            return "failed: %s" % exc, None
+
+    extra["cavity384_f64_mlups"] = quick(384, 384, "float64", "MRT", False, 1000, 50, "cavity384")[0]
+    # the reference's own published shape and default configuration (MRT_GPU.py:48-58: SRT, turb = 1, fp32, 640^2,
+    # 3000 iterations; BASELINE.md section 1: Tesla P100 384 true MLUPS, Xeon E5-2680 28 threads 21.9 MLUPS)
+    v, us = quick(640, 640, "float32", "SRT", True, 3000, 50, "refdefault640")
+    extra["refdefault640"] = {"mlups": v, "us_per_step": us, "config": "640x640 SRT turb=1 fp32, 3000 steps, device-resident",
+                              "published_P100_true_mlups": 384.0, "published_xeon28_mlups": 21.9,
+                              "vs_published_P100": round(v / 384.0, 1) if isinstance(v, float) else None}
+    extra["refdefault640_f64_mlups"] = quick(640, 640, "float64", "SRT", True, 3000, 50, "refdefault640")[0]
+    # Smagorinsky closure at the roofline size: 176 / 88 B per node and launch (two extra state values read and written)
+    for dt, key in (("float64", "turb4096_f64"), ("float32", "turb4096_f32")):
+        extra[key + "_srt_mlups"] = quick(nx, ny, dt, "SRT", True, max(args.steps // 5, 20), 5, wl)[0]
+        extra[key + "_srt_one_step_mlups"] = quick(nx, ny, dt, "SRT", True, max(args.steps // 5, 20), 5, wl, {"two_step": 0})[0]
+    # same-size single-GPU anchor of the N > 1 strong-scaling runs (2 x 77.3 GB of populations on one B200)
+    if wl == "cavity4096":
+        try:
+            free, _ = torch.cuda.mem_get_info()
+            if free > 165e9:
+                extra["cavity32768_f64_mlups"] = quick(32768, 32768, "float64", "MRT", False, 10, 3, "cavity32768")[0]
+            else:
+                extra["cavity32768_f64_mlups"] = "skipped: %.0f GB free" % (free / 1e9)
+        except Exception as exc:      # pragma: no cover
+            extra["cavity32768_f64_mlups"] = "failed: %s" % exc
+    # host link rate (pinned H2D / D2H of 1 GiB), the bound of the e2e number
     try:
-        n2, _, Re2, _ = WORKLOADS["cavity384"]
-        with L.CavitySolver(n2, n2, 1, "float64", "MRT", engine=args.engine) as s:
-            s.set_reynolds(Re2, 0.08); s.init_equilibrium(); s.step(50, write_macros=False, stream=stream)
-            ms2 = time_device_steps(lambda k: s.step(k, write_macros=False, stream=stream), torch.cuda.synchronize, 1000, torch)
-            extra["cavity384_f64_mlups"] = round(n2 * n2 * 1000 / ms2 / 1e3, 1)
+        hbuf = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+        dbuf = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+        rates = {}
+        for name, (a_, b_) in (("h2d", (dbuf, hbuf)), ("d2h", (hbuf, dbuf))):
+            a_.copy_(b_, non_blocking=True); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a_.copy_(b_, non_blocking=True); e1.record(); torch.cuda.synchronize()
+            rates[name] = round((1 << 30) / e0.elapsed_time(e1) / 1e6, 1)
+        extra["host_link_gbs"] = rates
+        e2e["copy_bound_seconds"] = round(h2d / rates["h2d"] / 1e9 + (rho_out.nbytes + u_out.nbytes) / rates["d2h"] / 1e9, 4)
+        del hbuf, dbuf
     except Exception as exc:      # pragma: no cover
-        extra["cavity384_error"] = str(exc)
+        extra["host_link_error"] = str(exc)
     # ---- CPU baseline (reference Cython step as shipped, bounded sample) -------------------------------------------
     try:
         cb, _, _ = cpu_baseline_sample("functions", Re, 12.0, 640)
@@ -293,22 +352,26 @@ def run_single_gpu(args):
     except Exception as exc:      # pragma: no cover
         cb = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "port", "sample": "failed: %s" % exc}
     r64, r32 = results["float64"], results["float32"]
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get("%s_float64" % wl)
+            tj = json.load(fh)
+            traffic = tj.get("%s_float64" % wl)
+            traffic_src = tj.get("source")
     except Exception:
         pass
     out = {"metric": "MLUPS", "value": round(r64["mlups"], 1), "unit": "MLUPS", "n_gpus": 1, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(r64["ms_per_step"], 5), "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": wl, "description": desc, "collision": "MRT", "engine": r64["engine"],
-                      "scaling_note": "N > 1 runs ONE 32768^2 cavity in y-strips (strong scaling); its single-GPU anchor is "
-                                      "`--workload cavity32768` (74 944 MLUPS); MLUPS is size-independent at these sizes",
+                      "scaling_note": "N > 1 runs ONE 32768^2 cavity in y-strips (strong scaling); its same-size single-GPU "
+                                      "anchor is measured in this run: extra.cavity32768_f64_mlups",
                       "l2": "state (2 x %.2f GB) far larger than the 126 MB L2: no flush needed" % (nx * ny * 72 / 1e9)},
            "roofline": {"bound": "hbm", "achieved": round(r64["gbs"], 1), "peak": peak, "unit": "GB/s",
                         "frac": round(r64["gbs"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                        "kernel": "lbm_step_fused2 (two lattice steps per launch)" if r64["steps_per_launch"] > 1.5 else "lbm_step_ldg",
+                        "traffic_source": traffic_src or "not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum "
+                                                         "per launch from the ncu capture summarised under profiles/",
+                        "kernel": "lbm_step_slide2 (two lattice steps per launch)" if r64["steps_per_launch"] > 1.5 else "lbm_step_ldg",
                         "algorithmic_bytes_per_node_per_launch": 144, "nodes_per_launch": nx * ny,
                         "steps_per_launch": round(r64["steps_per_launch"], 3),
                         "frac_of_nominal_8TBs": round(r64["gbs"] / 8000.0, 4),
@@ -323,7 +386,7 @@ def run_single_gpu(args):
                                 "f32": {"value": round(one_step["float32"]["mlups"], 1),
                                         "roofline_achieved": round(one_step["float32"]["gbs"], 1),
                                         "roofline_frac": round(one_step["float32"]["gbs"] / peak, 4)},
-                                "note": "LBM_B200_FUSED2=0: one step per launch, 144 / 72 B per node-step, HBM-bound"},
+                                "note": "tuning two_step=0: one step per launch, 144 / 72 B per node-step, HBM-bound"},
            "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "extra": extra}
     print(json.dumps(out), flush=True)
 
@@ -337,6 +400,19 @@ def run_multi_gpu(args, rank, world, local_rank):
     wl = args.workload or "cavity32768"
     nx, ny, Re, desc = WORKLOADS[wl]
     peak, peak_src = measured_peak()
+    # correctness of the real NCCL path before anything is timed: a 512 x 384 cavity in strips (one-step kernels at this
+    # size, then the sliding two-step kernel forced on the strips) must equal the single-GPU run bit for bit
+    import numpy as np
+    import latticeboltzmannsimulations_b200 as L
+    strips_ok = True
+    for tuning in (None, {"slide_min_nodes": 0, "slide_h": 14}):
+        chk = StripCavity(512, 384, 1000.0, 0.08, "float64", "MRT", overlap=not args.no_overlap, tuning=tuning)
+        chk.step(41, write_macros=True)
+        got = chk.gather_fields()
+        chk.close()
+        if rank == 0:
+            want = L.run_cavity(512, 384, 1000.0, steps=41, dtype="float64", return_f=True)
+            strips_ok = strips_ok and all(np.array_equal(a_, b_) for a_, b_ in zip(got, want))
     sc = StripCavity(nx, ny, Re, 0.08, "float64", "MRT", engine=args.engine, overlap=not args.no_overlap)
     sc.step(args.warmup)
     sc.sync()
@@ -390,7 +466,8 @@ def run_multi_gpu(args, rank, world, local_rank):
                           "decomposition": "%d y-strips of %d rows, 3 populations x %d values per interface and direction "
                                            "per step over NCCL send/recv, %s" % (
                                                world, sc.nyl, nx, "overlapped with the interior update" if sc.overlap else "not overlapped"),
-                          "note": "the N=1 line runs cavity4096 (config 3) with the same kernels; MLUPS per GPU is comparable",
+                          "note": "the N=1 line runs cavity4096 (config 3) with the same kernels and reports the same-size "
+                                  "single-GPU anchor as extra.cavity32768_f64_mlups",
                           "l2": "per-GPU state far larger than L2: no flush needed"},
                "roofline": {"bound": "hbm", "achieved": round(gbs / world, 1), "peak": peak, "unit": "GB/s",
                             "frac": round(gbs / world / peak, 4), "traffic": None, "peak_source": peak_src,
@@ -399,7 +476,10 @@ def run_multi_gpu(args, rank, world, local_rank):
                "e2e": {"value": round(nx * ny * args.steps / e2e_s / 1e6, 1), "unit": "MLUPS", "h2d_bytes_per_step": 0,
                        "d2h_bytes_per_step": int((rho_out.nbytes + u_out.nbytes) * world / args.steps),
                        "call": "StripCavity.step(K, write_macros) + macros() -> pinned rho,u strips (init generated on device)"},
-               "gpu_launches": int(launches), "clocks": clocks}
+               "gpu_launches": int(launches), "clocks": clocks, "strips_bitwise_ok": bool(strips_ok),
+               "extra": {"halo": "nine rows per neighbour packed into one buffer: one NCCL send + one recv per interface "
+                                 "and (double) step" if sc.packed else "row views, nine sends per interface",
+                         "rows_per_strip": int(sc.nyl)}}
         print(json.dumps(out), flush=True)
     sc.close()
     dist.barrier()

@@ -148,6 +148,15 @@ int lbm_step2_available(lbm_handle_t h);
 /* Device pointers of the buffer being read (which = 0) / written (which = 1) by the next lbm_step_region. */
 int lbm_buffer_ptr(lbm_handle_t h, int which, void** ptr);
 
+/* The nine halo rows of one side as ONE contiguous device buffer buf[9][nx] (a single send / recv per neighbour
+ * instead of nine), for the buffer written by the (double) step in progress, i.e. before lbm_swap / lbm_swap2:
+ * pack gathers what goes to the strip above (dir = 0: populations {0,1,3,2,5,6} of the first row, {2,5,6} of the
+ * second) or below (dir = 1: {0,1,3,4,7,8} of the last row, {4,7,8} of the row before it); unpack scatters what came
+ * from the strip above (dir = 0) / below (dir = 1) into the ghost row and the second ghost rows of that side.
+ * Single-cavity strips of >= 2 rows.  (No reference counterpart: the upstream solvers are single-GPU.) */
+int lbm_halo_pack(lbm_handle_t h, int dir, void* buf, void* stream);
+int lbm_halo_unpack(lbm_handle_t h, int dir, const void* buf, void* stream);
+
 /* cuda.memcpy_dtoh(rho, rho_g) / (u, u_g) + transposes (MRT_GPU.py:756-760): rho [batch][nx][ny_local],
  * u [batch][2][nx][ny_local].  Either pointer may be NULL. */
 int lbm_get_macros(lbm_handle_t h, void* rho, void* u, int on_device, void* stream);

@@ -1035,6 +1035,56 @@ int lbm_swap2(lbm_handle_t s) {
     return LBM_OK;
 }
 
+// Stored rows and populations of the nine halo rows on one side (order of distributed.halo_plan(deep=True)):
+// send: up {0,1,3,2,5,6} of local row 0 + {2,5,6} of local row 1; down {0,1,3,4,7,8} of row nyl-1 + {4,7,8} of nyl-2.
+// recv: the same populations land in the ghost row of that side and in its three second ghost rows.
+static HaloRows halo_rows(const lbm_solver* s, int dir, bool pack) {
+    static const int up[9] = {0, 1, 3, 2, 5, 6, 2, 5, 6}, dn[9] = {0, 1, 3, 4, 7, 8, 4, 7, 8};
+    HaloRows h{};
+    for (int i = 0; i < 9; ++i) {
+        if (pack) {
+            h.pop[i] = dir == 0 ? up[i] : dn[i];
+            h.row[i] = dir == 0 ? (i < 6 ? 1 : 2) : (i < 6 ? s->nyl : s->nyl - 1);       // stored row = local row + 1
+        } else {        // what arrives from above are the neighbour's DOWN-going rows, and vice versa
+            h.pop[i] = dir == 0 ? dn[i] : up[i];
+            h.row[i] = dir == 0 ? 0 : s->nyl + 1;
+        }
+    }
+    return h;
+}
+
+static int halo_move(lbm_solver* s, int dir, void* buf, bool pack, cudaStream_t st) {
+    if (!buf) return fail(LBM_EINVAL, "NULL buffer");
+    if (dir != 0 && dir != 1) return fail(LBM_EINVAL, "dir must be 0 (strip above) or 1 (strip below)");
+    if (s->cfg.batch != 1 || s->nyl < 2) return fail(LBM_ESTATE, "packed halo rows need a single-cavity strip of >= 2 rows");
+    int rc = set_device(s);
+    if (rc) return rc;
+    char* f = (char*)s->f[s->cur ^ 1];                                  // the buffer written by the step in progress
+    char* g2 = f + ((size_t)s->cfg.batch * s->cavity + (size_t)dir * 3 * s->pitch) * s->esz;
+    const HaloRows h = halo_rows(s, dir, pack);
+    dim3 grid((s->cfg.nx + 255) / 256, 9);
+    if (s->esz == 8) {
+        if (pack) lbm_halo_rows<double, true><<<grid, 256, 0, st>>>((double*)f, (double*)g2, (double*)buf, h, s->cfg.nx, s->pitch, s->plane);
+        else lbm_halo_rows<double, false><<<grid, 256, 0, st>>>((double*)f, (double*)g2, (double*)buf, h, s->cfg.nx, s->pitch, s->plane);
+    } else {
+        if (pack) lbm_halo_rows<float, true><<<grid, 256, 0, st>>>((float*)f, (float*)g2, (float*)buf, h, s->cfg.nx, s->pitch, s->plane);
+        else lbm_halo_rows<float, false><<<grid, 256, 0, st>>>((float*)f, (float*)g2, (float*)buf, h, s->cfg.nx, s->pitch, s->plane);
+    }
+    s->launches++;
+    CK(cudaGetLastError());
+    return LBM_OK;
+}
+
+int lbm_halo_pack(lbm_handle_t s, int dir, void* buf, void* stream) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    return halo_move(s, dir, buf, true, (cudaStream_t)stream);
+}
+
+int lbm_halo_unpack(lbm_handle_t s, int dir, const void* buf, void* stream) {
+    if (!s) return fail(LBM_EINVAL, "NULL handle");
+    return halo_move(s, dir, const_cast<void*>(buf), false, (cudaStream_t)stream);
+}
+
 int lbm_buffer_ptr(lbm_handle_t s, int which, void** ptr) {
     if (!s || !ptr) return fail(LBM_EINVAL, "NULL argument");
     *ptr = s->f[which ? (s->cur ^ 1) : s->cur];

@@ -514,6 +514,21 @@ __global__ void lbm_sum_u(const T* __restrict__ ux, const T* __restrict__ uy, do
     }
 }
 
+// Halo rows of a y-strip <-> one contiguous buffer [9][nx] per neighbour (a single NCCL send / recv instead of nine).
+// Row i of the buffer is row `row[i]` of population `pop[i]` of the strip buffer (PACK), or -- UNPACK -- the ghost row
+// (i < 6) / the i-6-th second ghost row (i >= 6) on that side.  Order = distributed.halo_plan(deep=True).
+struct HaloRows { int pop[9]; int row[9]; };
+template <typename T, bool PACK>
+__global__ void lbm_halo_rows(T* __restrict__ strip, T* __restrict__ g2side, T* __restrict__ buf, HaloRows h, int nx, int pitch,
+                              long long plane) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nx) return;
+    const int i = blockIdx.y;
+    T* p = (!PACK && i >= 6) ? g2side + (long long)(i - 6) * pitch : strip + h.pop[i] * plane + (long long)h.row[i] * pitch;
+    if (PACK) buf[(long long)i * nx + x] = p[x];
+    else p[x] = buf[(long long)i * nx + x];
+}
+
 // The stopping rule of MRT_GPU_datagen.py:726-733 for every cavity of a batch, on the device: one thread per cavity
 // compares the mean of the stored velocity field with the one of the previous check, counts the hits (never reset, as
 // in the reference) and retires the cavity when the count exceeds hits - 1.  newly[b] = 1 marks cavities retired by

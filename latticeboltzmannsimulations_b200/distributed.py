@@ -143,7 +143,8 @@ class StripCavity:
     """One cavity decomposed into y-strips over the ranks of ``group`` (one CUDA device per rank)."""
 
     def __init__(self, nx: int, ny: int, Re: float, uLB: float = 0.08, dtype="float64", collision: str = "MRT",
-                 group=None, device: Optional[int] = None, engine: str = "auto", overlap: bool = True):
+                 group=None, device: Optional[int] = None, engine: str = "auto", overlap: bool = True,
+                 tuning: Optional[dict] = None):
         import torch
         import torch.distributed as dist
         from .solver import CavitySolver, _dtype_name
@@ -161,7 +162,7 @@ class StripCavity:
         with torch.cuda.device(self.device):
             self._raw = [torch.zeros(nbytes // esz, dtype=tdt, device="cuda") for _ in range(2)]
         self.solver = CavitySolver(nx, ny, 1, dtype, collision, y0=self.y0, ny_local=self.nyl, device=self.device,
-                                   engine=engine, ext_buffers=[t.data_ptr() for t in self._raw])
+                                   engine=engine, ext_buffers=[t.data_ptr() for t in self._raw], tuning=tuning)
         lay = self.solver.layout
         self.buffers = [strip_views(t, lay) for t in self._raw]
         self.solver.set_reynolds(Re, uLB)
@@ -170,6 +171,19 @@ class StripCavity:
         # the deep plan (what the two-step kernel needs) whenever every strip has at least two rows
         self.deep = all(n >= 2 for _, n in self.parts)
         self.halo = HaloExchanger(self.buffers, nx, self.rank, self.world, group, deep=self.deep)
+        # packed exchange (deep plan only): the nine rows per neighbour travel as ONE contiguous buffer, gathered /
+        # scattered by lbm_halo_pack / lbm_halo_unpack -> one send + one recv per interface instead of nine each
+        self.packed = self.deep and self.world > 1
+        self._pack_ops = []
+        if self.packed:
+            with torch.cuda.device(self.device):
+                self._sbuf = [torch.zeros(9, nx, dtype=tdt, device="cuda") for _ in range(2)]   # to above / to below
+                self._rbuf = [torch.zeros(9, nx, dtype=tdt, device="cuda") for _ in range(2)]   # from above / from below
+            self._sides = [d for d, ok in ((0, self.rank > 0), (1, self.rank < self.world - 1)) if ok]
+            for d in self._sides:
+                peer = self.rank - 1 if d == 0 else self.rank + 1
+                self._pack_ops.append(dist.P2POp(dist.isend, self._sbuf[d], peer, group=group))
+                self._pack_ops.append(dist.P2POp(dist.irecv, self._rbuf[d], peer, group=group))
         self.overlap = overlap and self.nyl >= 5
         with torch.cuda.device(self.device):
             self.s_main = torch.cuda.Stream()
@@ -178,11 +192,28 @@ class StripCavity:
             self.ev_halo = torch.cuda.Event()
             self.ev_main.record(torch.cuda.current_stream())
             self.ev_halo.record(torch.cuda.current_stream())
+            # two events per stream, used alternately (the wait of pass n+1 is enqueued before pass n+2 re-records)
+            self._evs_main = [torch.cuda.Event(), torch.cuda.Event()]
+            self._evs_halo = [torch.cuda.Event(), torch.cuda.Event()]
         self.steps_done = 0
         self.passes_done = 0          # launches of the whole strip (a two-step pass counts once)
 
     def _dst_index(self) -> int:
         return self._ptr[self.solver.buffer_ptr(1)]
+
+    def _exchange(self, dst: int, stream) -> None:
+        """Halo exchange of the buffer being written, enqueued on ``stream`` (the host does not wait)."""
+        s = self.solver
+        if self.packed:
+            for d in self._sides:
+                s.halo_pack(d, self._sbuf[d].data_ptr(), stream.cuda_stream)
+            for w in self.dist.batch_isend_irecv(self._pack_ops):
+                w.wait()
+            for d in self._sides:
+                s.halo_unpack(d, self._rbuf[d].data_ptr(), stream.cuda_stream)
+        else:
+            for w in self.halo.exchange(dst):
+                w.wait()
 
     def step(self, nsteps: int = 1, write_macros: bool = False) -> None:
         """Advance ``nsteps`` steps; two at a time with the temporal-blocking kernel when it is available (every
@@ -197,24 +228,23 @@ class StripCavity:
             region = s.step2_region if two else s.step_region
             dst = self._dst_index()
             if self.overlap:
+                k = self.passes_done & 1
                 with torch.cuda.stream(self.s_halo):
                     self.s_halo.wait_event(self.ev_main)              # interior of the previous step
                     region(_capi.LBM_REGION_EDGE, wm, self.s_halo.cuda_stream)
-                    for w in self.halo.exchange(dst):
-                        w.wait()                                       # stream-side wait, the host runs ahead
-                    new_halo = torch.cuda.Event()
+                    self._exchange(dst, self.s_halo)                  # stream-side waits only, the host runs ahead
+                    new_halo = self._evs_halo[k]
                     new_halo.record(self.s_halo)
                 with torch.cuda.stream(self.s_main):
                     self.s_main.wait_event(self.ev_halo)              # edge rows + halo of the previous step
                     region(_capi.LBM_REGION_INTERIOR, wm, self.s_main.cuda_stream)
-                    new_main = torch.cuda.Event()
+                    new_main = self._evs_main[k]
                     new_main.record(self.s_main)
                 self.ev_halo, self.ev_main = new_halo, new_main
             else:
                 with torch.cuda.stream(self.s_main):
                     region(_capi.LBM_REGION_ALL, wm, self.s_main.cuda_stream)
-                    for w in self.halo.exchange(dst):
-                        w.wait()
+                    self._exchange(dst, self.s_main)
             if two:
                 s.swap2()
             else:

@@ -186,6 +186,14 @@ class CavitySolver:
         _capi.check(self._lib.lbm_buffer_ptr(self._h, int(which), C.byref(p)))
         return int(p.value)
 
+    def halo_pack(self, direction: int, buf_ptr: int, stream: int = 0) -> None:
+        """Nine halo rows for the strip above (0) / below (1) -> one contiguous device buffer ``[9, nx]``."""
+        _capi.check(self._lib.lbm_halo_pack(self._h, int(direction), C.c_void_p(buf_ptr), C.c_void_p(stream)))
+
+    def halo_unpack(self, direction: int, buf_ptr: int, stream: int = 0) -> None:
+        """One contiguous buffer received from the strip above (0) / below (1) -> ghost rows of that side."""
+        _capi.check(self._lib.lbm_halo_unpack(self._h, int(direction), C.c_void_p(buf_ptr), C.c_void_p(stream)))
+
     def macros(self, current: bool = False, rho_out=None, u_out=None, stream: int = 0):
         """(rho[nx,ny], u[2,nx,ny]) -- by default with the reference's one-step lag (moments of the state that
         entered the last step, MRT_GPU.py:616-631 + :756-757); ``current=True`` evaluates the present state."""

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run_strips_one_gpu(nx, ny, world, Re, steps, dtype, split_regions, two_step=True, tuning=None):
+def _run_strips_one_gpu(nx, ny, world, Re, steps, dtype, split_regions, two_step=True, tuning=None, packed=False):
     import torch
     import latticeboltzmannsimulations_b200 as L
     from latticeboltzmannsimulations_b200 import _capi
@@ -46,7 +46,19 @@ def _run_strips_one_gpu(nx, ny, world, Re, steps, dtype, split_regions, two_step
             region = s.step2_region if two else s.step_region
             region(_capi.LBM_REGION_EDGE if do_split else _capi.LBM_REGION_ALL, wm)
         torch.cuda.synchronize()
-        exchange_local(plans, [views[r][dst[r]] for r in range(world)], nx)
+        if packed and deep:
+            # the packed exchange of StripCavity: nine rows per neighbour through one contiguous buffer
+            bufs = {(r, d): torch.empty(9, nx, dtype=tdt, device="cuda") for r in range(world) for d in (0, 1)}
+            for r in range(world):
+                for d in ((0,) if r > 0 else ()) + ((1,) if r < world - 1 else ()):
+                    solvers[r].halo_pack(d, bufs[(r, d)].data_ptr())
+            for r in range(world):
+                if r > 0:
+                    solvers[r].halo_unpack(0, bufs[(r - 1, 1)].data_ptr())      # what the strip above sent down
+                if r < world - 1:
+                    solvers[r].halo_unpack(1, bufs[(r + 1, 0)].data_ptr())      # what the strip below sent up
+        else:
+            exchange_local(plans, [views[r][dst[r]] for r in range(world)], nx)
         torch.cuda.synchronize()
         if do_split:
             for s in solvers:
@@ -92,6 +104,9 @@ def test_two_step_kernel_on_strips_bitwise(nx, ny, world, split, steps, dtype, t
     if dtype == "float64" or tuning is not None:           # (fp32 takes no tiles; the sliding kernel serves both)
         assert got[3] >= (steps - 1) // 2                  # the two-step kernel really ran
     for a, b in zip(got[:3], want):
+        assert np.array_equal(a, b)
+    packed = _run_strips_one_gpu(nx, ny, world, 1000, steps, dtype, split, tuning=tuning, packed=True)
+    for a, b in zip(packed[:3], want):
         assert np.array_equal(a, b)
     if tuning is not None:
         return

@@ -16,16 +16,21 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 ok = True
+SLIDE = {"slide_min_nodes": 0, "slide_h": 14}            # the sliding two-step kernel forced onto small strips
 for dtype in ("float64", "float32"):
-    for (nx, ny, steps, overlap) in [(256, 192, 80, True), (130, 67, 40, True), (512, 512, 50, False)]:
-        sc = StripCavity(nx, ny, 1000.0, 0.08, dtype, "MRT", overlap=overlap)
+    for (nx, ny, steps, overlap, tuning) in [(256, 192, 80, True, None), (130, 67, 40, True, None), (512, 512, 50, False, None),
+                                             (512, 384, 41, True, SLIDE), (700, 300, 30, False, SLIDE),
+                                             (1536, 1400, 21, True, None)]:
+        sc = StripCavity(nx, ny, 1000.0, 0.08, dtype, "MRT", overlap=overlap, tuning=tuning)
         sc.step(steps, write_macros=True)
         got = sc.gather_fields()
+        packed = sc.packed
         sc.close()
         if rank == 0:
             want = L.run_cavity(nx, ny, 1000.0, steps=steps, dtype=dtype, return_f=True)
             same = all(np.array_equal(a, b) for a, b in zip(got, want))
-            print("strips", dtype, nx, ny, steps, "overlap" if overlap else "serial", "bitwise equal:", same, flush=True)
+            print("strips", dtype, nx, ny, steps, "overlap" if overlap else "serial", "packed halo" if packed else "row views",
+                  "slide forced" if tuning else "default kernels", "bitwise equal:", same, flush=True)
             ok = ok and same
 # sharded sweep: each cavity equals its standalone run
 Re = [100.0 + 50 * i for i in range(2 * world + 1)]
