@@ -391,12 +391,17 @@ def run_single_gpu(args):
     print(json.dumps(out), flush=True)
 
 
+def _nccl_options():
+    from latticeboltzmannsimulations_b200.distributed import nccl_options
+    return nccl_options()
+
+
 def run_multi_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from latticeboltzmannsimulations_b200.distributed import StripCavity
     torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=_nccl_options())
     wl = args.workload or "cavity32768"
     nx, ny, Re, desc = WORKLOADS[wl]
     peak, peak_src = measured_peak()
@@ -495,7 +500,7 @@ def run_datagen(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=_nccl_options())
     nx, ny, _, desc = WORKLOADS["datagen256"]
     Re_all = np.linspace(100.0, 10000.0, 256)
     mine = shard_indices(256, rank, world)

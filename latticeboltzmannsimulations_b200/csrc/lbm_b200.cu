@@ -395,7 +395,9 @@ static bool fused2_usable(const lbm_solver* s) { return fused2_capable(s) && s->
 // Rows per segment of the sliding-window kernel: 4m - 2 (m iterations of four rows cover the segment and its two halo
 // rows exactly).  Short segments pay their start-up (two halo rows, an empty pipeline) more often, long ones leave a
 // long under-occupied tail at the end of the launch; measured optima (4096^2: 46 fp64 / 30 fp32) follow
-// 2 sqrt(rows per resident CTA slot).  Around that height pick the one whose CTA count fills whole waves best.
+// 2 sqrt(rows per resident CTA slot) -- up to about 48: wide / tall cavities do not want taller segments (32768 x 4096
+// fp64: 89 041 MLUPS at 46, 84 254 at 162, 81 683 at 254; tools/wide_sweep.py).  Around that height pick the one whose
+// CTA count fills whole waves best.
 static int slide_seg_h(const lbm_solver* s) {
     if (s->slide_h > 0) return s->slide_h;
     const int tx = 512 / s->esz;
@@ -403,7 +405,7 @@ static int slide_seg_h(const lbm_solver* s) {
     const long long slots = 3LL * s->num_sms;
     const double rows_per_slot = (double)nsx * s->nyl * s->cfg.batch / (double)slots;
     double h0 = 2.0 * sqrt(rows_per_slot);
-    h0 = h0 < 14.0 ? 14.0 : (h0 > 254.0 ? 254.0 : h0);
+    h0 = h0 < 14.0 ? 14.0 : (h0 > 48.0 ? 48.0 : h0);
     int best = 14;
     double best_eff = -1.0;
     for (int h = 14; h <= 254; h += 4) {

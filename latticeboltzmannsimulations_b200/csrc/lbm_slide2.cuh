@@ -286,22 +286,22 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
     int buf = 0;
     unsigned it = 0;                                               // iteration count: parities of the barriers
     for (int s = s0; s <= yb; s += R, ++it) {
-        slide_mbar_wait(bar_full + 8 * buf, (it >> 1) & 1);        // the staged rows of this iteration have landed
         const T* S = stg + buf * Cfg::STAGE;
         const int gys = a.y0 + s;
         // ---- sub-step 1: rows [s, s+R) x columns [x0-1, x0+TX] -> window ----
         // no wall node among the main items of this iteration (rows s .. s+R-1, columns x0 .. x0+TX-1), all exist
         const bool inner1 = x0 > 0 && x0 + TX - 1 < a.nx - 1 && gys > 0 && gys + R - 1 < a.ny - 1 && s + R - 1 <= yb;
+        AT pi0, rp0;
+        if (TURB && main_item && inner1) {                         // Smagorinsky state t-1 of this item's nodes: plain
+            const long long m = (long long)(s + ij) * pitch + (x0 + itx);      // loads, in flight during the wait below
+            pi0 = Item::ld(pi_in + m);
+            rp0 = Item::ld(rp_in + m);
+        }
+        slide_mbar_wait(bar_full + 8 * buf, (it >> 1) & 1);        // the staged rows of this iteration have landed
         int ws = wbase + ij;
         ws = ws >= WR ? ws - WR : ws;
         T* w = win + ws * WW + ilx + WOFF;
         if (main_item && inner1) {
-            AT pi0, rp0;
-            if (TURB) {                                            // state t-1 of this item's nodes
-                const long long m = (long long)(s + ij) * pitch + (x0 + itx);
-                pi0 = Item::ld(pi_in + m);
-                rp0 = Item::ld(rp_in + m);
-            }
             const T* c = S + ij * SW + ilx + (A - 1);              // first node of the item in population 0's staged rows
             AT f[9];
             f[0] = Item::ld(c);

@@ -27,6 +27,20 @@ UP_POPS = (2, 5, 6)      # c_y = +1: move to y-1, i.e. to the strip above (small
 DOWN_POPS = (4, 7, 8)    # c_y = -1: move to y+1, i.e. to the strip below
 
 
+def nccl_options():
+    """Process-group options for the y-strip driver: NCCL's internal stream at high priority.  torch runs the grouped
+    send / recv on that stream, not on the caller's; at default priority its kernel queues behind every CTA of the
+    interior launch (measured: the exchange then ends with the interior, a 45 us bubble per pass); at high priority it
+    slips in between, like the edge launches.  Returns None where torch has no such option."""
+    try:
+        import torch.distributed as dist
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        return opts
+    except Exception:     # pragma: no cover
+        return None
+
+
 def partition_rows(ny: int, world: int) -> List[Tuple[int, int]]:
     """Contiguous strips [(y0, ny_local)] -- the first ``ny % world`` ranks get one extra row."""
     if world < 1 or ny < world:
@@ -197,6 +211,7 @@ class StripCavity:
             self._evs_halo = [torch.cuda.Event(), torch.cuda.Event()]
         self.steps_done = 0
         self.passes_done = 0          # launches of the whole strip (a two-step pass counts once)
+        self.timeline = None          # set to [] to record CUDA events around the phases of every pass (tools/strip_timeline.py)
 
     def _dst_index(self) -> int:
         return self._ptr[self.solver.buffer_ptr(1)]
@@ -229,15 +244,26 @@ class StripCavity:
             dst = self._dst_index()
             if self.overlap:
                 k = self.passes_done & 1
+                tl = None
+                if self.timeline is not None:
+                    tl = {name: torch.cuda.Event(enable_timing=True) for name in
+                          ("edge0", "edge1", "xchg1", "int0", "int1")}
+                    tl["steps"] = n
+                    self.timeline.append(tl)
                 with torch.cuda.stream(self.s_halo):
                     self.s_halo.wait_event(self.ev_main)              # interior of the previous step
+                    if tl: tl["edge0"].record(self.s_halo)
                     region(_capi.LBM_REGION_EDGE, wm, self.s_halo.cuda_stream)
+                    if tl: tl["edge1"].record(self.s_halo)
                     self._exchange(dst, self.s_halo)                  # stream-side waits only, the host runs ahead
+                    if tl: tl["xchg1"].record(self.s_halo)
                     new_halo = self._evs_halo[k]
                     new_halo.record(self.s_halo)
                 with torch.cuda.stream(self.s_main):
                     self.s_main.wait_event(self.ev_halo)              # edge rows + halo of the previous step
+                    if tl: tl["int0"].record(self.s_main)
                     region(_capi.LBM_REGION_INTERIOR, wm, self.s_main.cuda_stream)
+                    if tl: tl["int1"].record(self.s_main)
                     new_main = self._evs_main[k]
                     new_main.record(self.s_main)
                 self.ev_halo, self.ev_main = new_halo, new_main

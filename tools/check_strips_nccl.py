@@ -9,11 +9,11 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import latticeboltzmannsimulations_b200 as L
-from latticeboltzmannsimulations_b200.distributed import StripCavity, datagen_sharded
+from latticeboltzmannsimulations_b200.distributed import StripCavity, nccl_options, datagen_sharded
 
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=nccl_options())
 rank, world = dist.get_rank(), dist.get_world_size()
 ok = True
 SLIDE = {"slide_min_nodes": 0, "slide_h": 14}            # the sliding two-step kernel forced onto small strips
