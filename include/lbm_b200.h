@@ -97,10 +97,6 @@ int lbm_get_layout(lbm_handle_t h, lbm_layout_t* out);
  *   "slide"               0 = never use the sliding-window two-step kernel (default 1)
  *   "slide_min_nodes"     smallest batch x nx x ny that uses it instead of the shared-memory tiles (default 2000000)
  *   "slide_h"             rows per segment of the sliding-window kernel, 0 = automatic
- *   "march"               1 = use the marching two-step kernel (default 0; the only two-step kernel for turb = 1)
- *   "march_min_nodes"     smallest batch x nx x ny that uses it (default 600000)
- *   "march_variant"       compiled (nodes per lane, register budget) variant, 0 = shipped default
- *   "march_h"             rows per segment, 0 = automatic
  *   "tile"                tile shape of the shared-memory two-step kernel, -1 = automatic
  *   "vec_f64", "vec_f32"  nodes per thread of the one-step kernels (1|2, 1|2|4)
  *   "graph", "pdl"        CUDA graphs for small cavities / programmatic dependent launch (default 1, 1)

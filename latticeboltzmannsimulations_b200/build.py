@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "liblbm_b200.so")
-SOURCES = ["lbm_b200.cu", "lbm_march2_f64.cu", "lbm_march2_f32.cu", "lbm_slide2_f64.cu", "lbm_slide2_f32.cu"]      # compiled in parallel, then linked
+SOURCES = ["lbm_b200.cu", "lbm_slide2_f64.cu", "lbm_slide2_f32.cu"]      # compiled in parallel, then linked
 HEADERS = [os.path.join("..", "..", "include", "lbm_b200.h")]                # + every .cuh / .h in csrc
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: no implicit contraction; every fused multiply-add is explicit in lbm_device.cuh, so that what a node

@@ -28,12 +28,6 @@
 
 using namespace lbm;
 
-namespace lbm {
-int march2_variants_f64(); int march2_cols_f64(int);
-int march2_variants_f32(); int march2_cols_f32(int);
-int march2_variants(int esz) { return esz == 8 ? march2_variants_f64() : march2_variants_f32(); }
-int march2_cols(int esz, int variant) { return esz == 8 ? march2_cols_f64(variant) : march2_cols_f32(variant); }
-}  // namespace lbm
 
 // ------------------------------------------------------------------------------------------------------------
 // error handling
@@ -58,13 +52,10 @@ static int fail(int code, const std::string& msg) {
 #define LBM_FUSED2_MIN_NODES 10000
 #define LBM_FUSED2_SMALL_NODES 250000     // below: 32x8 tiles
 #define LBM_FUSED2_LARGE_NODES 600000     // from here: 64x8 (fp64) / 32x16 (fp32) tiles
-// From here the marching two-step kernel (lbm_march2.cuh: one warp per x-strip segment, rolling register window)
-// replaces the shared-memory tiles; it also covers the Smagorinsky closure and batches with frozen cavities.
-#define LBM_MARCH_MIN_NODES 600000
 // The sliding-window two-step kernel (lbm_slide2.cuh: one CTA per column strip, bulk-copy double-buffered source rows)
 // takes over where its segments fill the machine (tools/size_sweep2.py: 1024^2 tiles 63 545 / sliding 59 332 MLUPS fp64,
-// 2048^2 70 677 / 74 571, 32 x 384^2 66 741 / 70 942; fp32 2048^2 100 744 / 125 098); the marching kernel then only
-// serves the Smagorinsky closure.
+// 2048^2 70 677 / 74 571, 32 x 384^2 66 741 / 70 942; fp32 2048^2 100 744 / 125 098).  It also covers the Smagorinsky
+// closure (whole cavities) and batches with frozen cavities, which the tiles do not.
 #define LBM_SLIDE_MIN_NODES 2000000
 
 // ------------------------------------------------------------------------------------------------------------
@@ -119,10 +110,6 @@ struct lbm_solver {
     int side = 0;              // which half of the double-buffered rho_lid / carry arrays is current
     int fused2_tile = -1;      // tile-shape variant of the fused kernel (-1 = per-dtype default)
     long long fused2_min_nodes = LBM_FUSED2_MIN_NODES;
-    int use_march = 0;         // marching two-step kernel (optional: slower than the one-step kernels with turb = 1)
-    int march_variant = 0;     // compiled (nodes per lane, register budget) variant, 0 = shipped default
-    int march_h = 0;           // rows per segment, 0 = chosen from the number of work items
-    long long march_min_nodes = LBM_MARCH_MIN_NODES;
     int use_slide = 1;         // sliding-window two-step kernel for large cavities / batches (no closure)
     int slide_h = 0;           // rows per segment, 0 = chosen from the number of work items
     long long slide_min_nodes = LBM_SLIDE_MIN_NODES;
@@ -369,7 +356,7 @@ static void launch_vec_coll(int coll, const StepArgs& a, const Launch& L, bool m
 }
 
 // Which two-step (temporal blocking) kernel advances this handle, if any (whole cavity or y-strip of >= 2 rows).
-enum { TWO_NONE = 0, TWO_TILE = 1, TWO_MARCH = 2, TWO_SLIDE = 3 };
+enum { TWO_NONE = 0, TWO_TILE = 1, TWO_SLIDE = 3 };
 static int two_step_kind(const lbm_solver* s) {
     if (!s->use_fused2 || s->engine != LBM_ENGINE_LDG || s->cfg.semantics != LBM_SEMANTICS_C || s->nyl < 2) return TWO_NONE;
     const long long nodes = (long long)s->cfg.nx * s->cfg.ny * s->cfg.batch;
@@ -377,8 +364,6 @@ static int two_step_kind(const lbm_solver* s) {
     const bool whole = s->nyl == s->cfg.ny;
     // the closure's per-node state has no halo exchange: two-step with turb = 1 on whole cavities only
     if (s->use_slide && nodes >= s->slide_min_nodes && (!s->cfg.turb || whole)) return TWO_SLIDE;
-    // the closure's per-node state has no halo exchange: two-step with turb = 1 on whole cavities only
-    if (s->use_march && nodes >= s->march_min_nodes && (!s->cfg.turb || whole)) return TWO_MARCH;
     // shared-memory tiles: no closure, no frozen cavities
     if (s->cfg.turb || s->active) return TWO_NONE;
     // fp32 never gains from the tiles (ALU-bound): 1024^2 one-step 107 088 / tiles 98 466 MLUPS, narrower cavities alike
@@ -390,8 +375,6 @@ static bool fused2_capable(const lbm_solver* s) { return two_step_kind(s) != TWO
 // ... and to lbm_step, which owns whole cavities only
 static bool fused2_usable(const lbm_solver* s) { return fused2_capable(s) && s->nyl == s->cfg.ny; }
 
-// Rows per segment of the marching kernel: as tall as possible (a segment recomputes one row above and below
-// itself) while the launch still has a few work items per resident warp slot.
 // Rows per segment of the sliding-window kernel: 4m - 2 (m iterations of four rows cover the segment and its two halo
 // rows exactly).  Short segments pay their start-up (two halo rows, an empty pipeline) more often, long ones leave a
 // long under-occupied tail at the end of the launch; measured optima (4096^2: 46 fp64 / 30 fp32) follow
@@ -416,16 +399,6 @@ static int slide_seg_h(const lbm_solver* s) {
         if (eff > best_eff + 1e-9) { best_eff = eff; best = h; }
     }
     return best;
-}
-
-static int march_seg_h(const lbm_solver* s) {
-    if (s->march_h > 0) return s->march_h;
-    const int cols = march2_cols(s->esz, s->march_variant);
-    const long long nsx = (s->cfg.nx + cols - 1) / cols;
-    const long long want = 3LL * s->num_sms * 16;
-    for (int h = 64; h > 8; h >>= 1)
-        if (nsx * ((s->nyl + h - 1) / h) * s->cfg.batch >= want) return h;
-    return 8;
 }
 
 // Tile-shape variant of the two-step kernel.  Defaults from tools/fused2_sweep.py at 4096^2: fp64 64x8 tiles at
@@ -483,7 +456,6 @@ static cudaError_t launch_fused2_t(lbm_solver* s, const StepArgs& a, bool macros
 
 // Tile height of the fused kernel in use (needed to cut a strip into edge / interior bands of whole tile rows).
 static int fused2_tile_height(const lbm_solver* s) {
-    if (two_step_kind(s) == TWO_MARCH) return march_seg_h(s);
     if (two_step_kind(s) == TWO_SLIDE) return slide_seg_h(s);
     switch (fused2_variant(s)) {
         case 1: case 3: case 9: return 8;
@@ -506,17 +478,6 @@ static int launch_fused2_rows(lbm_solver* s, int row_begin, int row_count, bool 
         L.turb = s->cfg.turb != 0; L.macros = macros; L.batch = s->cfg.batch; L.pdl = s->use_pdl != 0; L.st = st;
         e = s->esz == 8 ? launch_slide2_f64(a, L) : launch_slide2_f32(a, L);
         if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("sliding two-step launch: ") + cudaGetErrorString(e));
-        s->launches++;
-        return LBM_OK;
-    }
-    if (two_step_kind(s) == TWO_MARCH) {
-        a.seg_h = march_seg_h(s);
-        March2Launch L{};
-        L.coll = s->cfg.collision == LBM_SRT ? COLL_SRT : s->cfg.collision == LBM_TRT ? COLL_TRT : COLL_MRT;
-        L.turb = s->cfg.turb != 0; L.macros = macros; L.variant = s->march_variant; L.batch = s->cfg.batch;
-        L.pdl = s->use_pdl != 0; L.st = st;
-        e = s->esz == 8 ? launch_march2_f64(a, L) : launch_march2_f32(a, L);
-        if (e != cudaSuccess) return fail(LBM_ECUDA, std::string("marching two-step launch: ") + cudaGetErrorString(e));
         s->launches++;
         return LBM_OK;
     }
@@ -777,13 +738,6 @@ int lbm_set_tuning(lbm_handle_t s, const char* key, int64_t value) {
     const std::string k(key);
     const int v = (int)value;
     if (k == "two_step") s->use_fused2 = v != 0;
-    else if (k == "march") s->use_march = v != 0;
-    else if (k == "march_variant") {
-        if (v < 0 || march2_cols(s->esz, v) == 0) return fail(LBM_EINVAL, "march_variant out of range");
-        s->march_variant = v;
-    }
-    else if (k == "march_h") { if (v < 0 || v > 4096) return fail(LBM_EINVAL, "march_h must lie in [0, 4096]"); s->march_h = v; }
-    else if (k == "march_min_nodes") s->march_min_nodes = value;
     else if (k == "slide") s->use_slide = v != 0;
     else if (k == "slide_h") { if (v < 0 || v > 4096) return fail(LBM_EINVAL, "slide_h must lie in [0, 4096]"); s->slide_h = v; }
     else if (k == "slide_min_nodes") s->slide_min_nodes = value;

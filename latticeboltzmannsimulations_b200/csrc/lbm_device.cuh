@@ -49,7 +49,7 @@ struct StepArgs {
     long long mplane;          // macro plane = nyl * pitch elements
     int row_begin, row_stride; // local row of launch row 0 and distance between consecutive launch rows
     int row_count;             // launch rows (blockIdx.y * blockDim.y + threadIdx.y < row_count)
-    int seg_h, nsx;            // marching two-step kernel: rows per segment, number of x-strips (one warp each)
+    int seg_h;                 // sliding-window two-step kernel: rows per segment (one CTA each)
 };
 
 template <typename T>
@@ -68,7 +68,7 @@ template <typename T> __device__ __forceinline__ T w_diag() { return (T)(1.0 / 3
 // ---- rounding discipline ----------------------------------------------------------------------------------------
 // The library is compiled with -fmad=false: the compiler never contracts a*b+c on its own, every fused multiply-add
 // below is spelled fm(a, b, c).  What a node computes is therefore fixed by this file alone and does not depend on
-// which kernel inlines it -- the one-step, shared-memory-tile and marching kernels are bit-identical by construction
+// which kernel inlines it -- the one-step, shared-memory-tile and sliding-window kernels are bit-identical by construction
 // (with implicit contraction the fp64 SRT / TRT paths of two kernel families were seen to differ in the last bit).
 __device__ __forceinline__ float fm(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ double fm(double a, double b, double c) { return __fma_rn(a, b, c); }

@@ -484,19 +484,15 @@ def test_tma_engine_parity(dtype):
 
 @pytest.mark.parametrize("tuning", ["vec_f64=2,vec_f32=2", "vec_f32=1", "graph=0,pdl=0", "two_step=0", "tile=0", "tile=4",
                                     "slide_min_nodes=0", "slide_min_nodes=0,slide_h=14", "slide_min_nodes=0,slide_h=37",
-                                    "slide_min_nodes=0,slide_h=126", "slide=0,march=1,march_min_nodes=0",
-                                    "slide=0,march=1,march_min_nodes=0,march_variant=1",
-                                    "slide=0,march=1,march_min_nodes=0,march_variant=4,march_h=16",
-                                    "slide=0,march=1,march_min_nodes=0,march_variant=6,march_h=37"])
+                                    "slide_min_nodes=0,slide_h=126", "slide=0", "slide=0,tile=3"])
 def test_kernel_variants_are_bit_identical(tuning, monkeypatch):
     """Every compiled data-movement variant (scalar / 2 / 4 nodes per thread, with and without graphs and programmatic
     dependent launch, one-step kernels, shared-memory two-step tiles, the sliding-window two-step kernel at several
-    segment heights, variants and segment heights of the marching two-step kernel) produces the same bits as the
-    default configuration."""
+    segment heights) produces the same bits as the default configuration."""
     import latticeboltzmannsimulations_b200 as L
     # the later cases are above the size threshold of the two-step (temporal blocking) kernels; 70 and 71 steps end on
     # a macro-writing two-step launch and on a one-step launch respectively; turb = 1 exercises the double-buffered
-    # Smagorinsky state of the marching kernel
+    # Smagorinsky state of the sliding-window kernel
     cases = [("float64", 200, 90, "MRT", False), ("float32", 131, 77, "SRT", False), ("float32", 96, 64, "MRT", True),
              ("float64", 1000, 640, "MRT", False), ("float32", 1100, 600, "SRT", False), ("float64", 777, 801, "TRT", False),
              ("float32", 1001, 640, "MRT", False), ("float64", 930, 700, "SRT", True), ("float32", 1030, 610, "MRT", True)]
@@ -513,8 +509,8 @@ def test_kernel_variants_are_bit_identical(tuning, monkeypatch):
 def test_tuning_keys_are_validated():
     import latticeboltzmannsimulations_b200 as L
     with L.CavitySolver(64, 64) as s:
-        s.set_tuning("march_h", 16)
-        for key, val in (("no_such_key", 1), ("march_variant", 99), ("vec_f32", 3), ("tile", 17)):
+        s.set_tuning("slide_h", 16)
+        for key, val in (("no_such_key", 1), ("slide_h", -3), ("vec_f32", 3), ("tile", 17)):
             with pytest.raises(L.LBMError):
                 s.set_tuning(key, val)
 

@@ -21,7 +21,7 @@ for (nx, ny, batch) in [(128, 128, 1), (192, 192, 1), (384, 384, 1), (512, 512, 
     steps = 4000 if nx * ny * batch < 1e6 else (1000 if nx * ny * batch < 8e6 else 200)
     for dt in ("float64", "float32"):
         out = []
-        for name, tun in (("one", {"two_step": 0}), ("tile", {"slide": 0, "march": 0, "two_step_min_nodes": 0}),
+        for name, tun in (("one", {"two_step": 0}), ("tile", {"slide": 0, "two_step_min_nodes": 0}),
                           ("slide", {"slide_min_nodes": 0}), ("slide14", {"slide_min_nodes": 0, "slide_h": 14})):
             try:
                 m, ms = run(nx, ny, batch, dt, "MRT", False, tun, steps)

@@ -17,7 +17,7 @@ for (nx, steps) in ((4096, 200), (2048, 500), (1024, 2000), (640, 3000)):
     for dt in ("float64", "float32"):
         for coll, turb in (("SRT", True), ("MRT", True), ("SRT", False)):
             out = []
-            for name, tun in (("one", {"two_step": 0}), ("slide", {"slide_min_nodes": 0}), ("march", {"slide": 0, "march": 1, "march_min_nodes": 0})):
+            for name, tun in (("one", {"two_step": 0}), ("slide", {"slide_min_nodes": 0})):
                 m, ms = run(nx, nx, dt, coll, turb, tun, steps)
                 out.append("%s %.0f (%.1f us)" % (name, m, ms * 1e3))
             print("%d^2 %s %s turb=%d: %s" % (nx, dt, coll, turb, " | ".join(out)), flush=True)
