@@ -159,6 +159,11 @@ int lbm_get_macros(lbm_handle_t h, void* rho, void* u, int on_device, void* stre
 /* Same fields evaluated from the CURRENT populations (no one-step lag). */
 int lbm_get_macros_current(lbm_handle_t h, void* rho, void* u, int on_device, void* stream);
 
+/* The equilibrium of the stored (lagged) rho, u -- the `feq` that functions.allfunc returns next to them
+ * (functions.pyx:88, 222: equ(rho, u) of the step's own moments) -- computed on the device from the stored fields
+ * instead of sending rho, u back up: feq [batch][9][nx][ny_local]. */
+int lbm_get_feq(lbm_handle_t h, void* feq, int on_device, void* stream);
+
 /* functions.equ(rho, ux, uy) (functions.pyx:229-267, == MRT.py:213-231): second-order equilibrium of arbitrary
  * fields, stateless.  rho, ux, uy: [n] values; feq: [9][n]; dtype = lbm_dtype; on_device != 0 for device pointers. */
 int lbm_equilibrium(int dtype, int64_t n, const void* rho, const void* ux, const void* uy, void* feq,

@@ -26,7 +26,7 @@ SYMBOLS = [
     "lbm_last_error", "lbm_abi_version", "lbm_device_count", "lbm_state_bytes", "lbm_create", "lbm_destroy",
     "lbm_get_layout", "lbm_set_tuning", "lbm_set_reynolds", "lbm_set_rates", "lbm_init_equilibrium", "lbm_upload_f",
     "lbm_download_f", "lbm_step", "lbm_step_region", "lbm_swap", "lbm_step2_region", "lbm_swap2", "lbm_step2_available", "lbm_buffer_ptr", "lbm_halo_pack", "lbm_halo_unpack", "lbm_get_macros",
-    "lbm_get_macros_current", "lbm_equilibrium", "lbm_mean_u", "lbm_set_active", "lbm_converge_check", "lbm_diagnostics", "lbm_sync", "lbm_get_counters", "lbm_engine_name",
+    "lbm_get_macros_current", "lbm_get_feq", "lbm_equilibrium", "lbm_mean_u", "lbm_set_active", "lbm_converge_check", "lbm_diagnostics", "lbm_sync", "lbm_get_counters", "lbm_engine_name",
 ]
 
 
@@ -90,6 +90,7 @@ def load():
     lib.lbm_buffer_ptr.argtypes = [H, C.c_int, C.POINTER(C.c_void_p)]
     lib.lbm_get_macros.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.lbm_get_macros_current.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.lbm_get_feq.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p]
     lib.lbm_halo_pack.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]
     lib.lbm_halo_unpack.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]
     lib.lbm_equilibrium.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

@@ -87,7 +87,9 @@ struct lbm_solver {
     CavityParams* cav = nullptr;
     std::vector<CavityParams> cav_host;
     bool cav_dirty = true;
-    void* staging = nullptr;   // host-layout staging for uploads/downloads
+    void* staging = nullptr;   // host-layout staging for uploads/downloads (two plane-sized slots)
+    cudaStream_t copy_stream = nullptr;            // host link copies, overlapped with the transposes
+    cudaEvent_t ev_slot_full[2] = {nullptr, nullptr}, ev_slot_free[2] = {nullptr, nullptr};
     size_t staging_bytes = 0;
     void* scratch = nullptr;   // finalize target (populations) when B must stay intact
     int64_t steps = 0, launches = 0;
@@ -639,6 +641,10 @@ int lbm_destroy(lbm_handle_t s) {
     cudaFree(s->staging); cudaFree(s->scratch);
     for (int i = 0; i < 4; ++i) if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
     if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
+    if (s->copy_stream) {
+        cudaStreamDestroy(s->copy_stream);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(s->ev_slot_full[i]); cudaEventDestroy(s->ev_slot_free[i]); }
+    }
     delete s;
     return LBM_OK;
 }
@@ -825,34 +831,79 @@ static int ensure_staging(lbm_solver* s, size_t bytes) {
     return LBM_OK;
 }
 
+static void launch_transpose(lbm_solver* s, bool to_device, void* dev, void* lin, int planes, long long dev_plane_stride,
+                             long long dev_row0, cudaStream_t st) {
+    const int nx = s->cfg.nx, nyl = s->nyl;
+    dim3 blk(32, 8), grid((nx + 31) / 32, (nyl + 31) / 32, planes);
+    if (s->esz == 8) {
+        if (to_device) lbm_transpose<double, true><<<grid, blk, 0, st>>>((double*)dev, (double*)lin, nx, nyl, s->pitch, dev_plane_stride, dev_row0);
+        else lbm_transpose<double, false><<<grid, blk, 0, st>>>((double*)dev, (double*)lin, nx, nyl, s->pitch, dev_plane_stride, dev_row0);
+    } else {
+        if (to_device) lbm_transpose<float, true><<<grid, blk, 0, st>>>((float*)dev, (float*)lin, nx, nyl, s->pitch, dev_plane_stride, dev_row0);
+        else lbm_transpose<float, false><<<grid, blk, 0, st>>>((float*)dev, (float*)lin, nx, nyl, s->pitch, dev_plane_stride, dev_row0);
+    }
+    s->launches++;
+}
+
 // Move `ncav` cavities of `planes` [nx][nyl] planes each between a reference-layout array (`lin`: host, or device
 // when on_device) and device planes.  lin_cavity_bytes: distance between cavities in `lin`; dev_*_stride in elements;
 // dev_row0: element offset of local row 0 inside a device plane.
+// Host arrays go plane by plane through two device staging slots: the copy engine (internal copy stream) moves plane
+// i+1 over the host link while the transpose kernel of plane i runs on the caller's stream -- the layout change costs
+// no time on top of the copies.  Device-resident arrays are transposed in place by one launch per cavity.
 static int move_planes(lbm_solver* s, void* lin_base, size_t lin_cavity_bytes, bool on_device, bool to_device,
                        int ncav, int planes, void* dev_base, long long dev_plane_stride, long long dev_cavity_stride,
                        long long dev_row0, cudaStream_t st) {
     const int nx = s->cfg.nx, nyl = s->nyl;
-    const size_t cav_bytes = (size_t)planes * nx * nyl * s->esz;
-    dim3 blk(32, 8), grid((nx + 31) / 32, (nyl + 31) / 32, planes);
-    if (!on_device) { int rc = ensure_staging(s, cav_bytes); if (rc) return rc; }
-    for (int b = 0; b < ncav; ++b) {
-        char* h = (char*)lin_base + (size_t)b * lin_cavity_bytes;
-        void* lin = on_device ? (void*)h : s->staging;
-        char* dev = (char*)dev_base + (size_t)b * dev_cavity_stride * s->esz;
-        if (to_device && !on_device) CK(cudaMemcpyAsync(lin, h, cav_bytes, cudaMemcpyHostToDevice, st));
-        if (s->esz == 8) {
-            if (to_device) lbm_transpose<double, true><<<grid, blk, 0, st>>>((double*)dev, (double*)lin, nx, nyl, s->pitch, dev_plane_stride, dev_row0);
-            else lbm_transpose<double, false><<<grid, blk, 0, st>>>((double*)dev, (double*)lin, nx, nyl, s->pitch, dev_plane_stride, dev_row0);
-        } else {
-            if (to_device) lbm_transpose<float, true><<<grid, blk, 0, st>>>((float*)dev, (float*)lin, nx, nyl, s->pitch, dev_plane_stride, dev_row0);
-            else lbm_transpose<float, false><<<grid, blk, 0, st>>>((float*)dev, (float*)lin, nx, nyl, s->pitch, dev_plane_stride, dev_row0);
+    if (on_device) {
+        for (int b = 0; b < ncav; ++b) {
+            launch_transpose(s, to_device, (char*)dev_base + (size_t)b * dev_cavity_stride * s->esz,
+                             (char*)lin_base + (size_t)b * lin_cavity_bytes, planes, dev_plane_stride, dev_row0, st);
+            CK(cudaGetLastError());
         }
-        s->launches++;
-        CK(cudaGetLastError());
-        if (!to_device && !on_device) CK(cudaMemcpyAsync(h, lin, cav_bytes, cudaMemcpyDeviceToHost, st));
-        if (!on_device && b + 1 < ncav) CK(cudaStreamSynchronize(st));   // staging is reused by the next cavity
+        return LBM_OK;
     }
-    if (!on_device) CK(cudaStreamSynchronize(st));
+    const size_t pbytes = (size_t)nx * nyl * s->esz;                     // one plane in the reference layout
+    int rc = ensure_staging(s, 2 * pbytes);
+    if (rc) return rc;
+    if (!s->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&s->ev_slot_full[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s->ev_slot_free[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t cs = s->copy_stream;
+    // the copy stream starts after everything already queued on the caller's stream (e.g. the finalize pass)
+    CK(cudaEventRecord(s->ev_slot_free[0], st));
+    CK(cudaStreamWaitEvent(cs, s->ev_slot_free[0], 0));
+    int i = 0;
+    for (int b = 0; b < ncav; ++b) {
+        for (int k = 0; k < planes; ++k, ++i) {
+            const int slot = i & 1;
+            char* h = (char*)lin_base + (size_t)b * lin_cavity_bytes + (size_t)k * pbytes;
+            char* lin = (char*)s->staging + (size_t)slot * pbytes;
+            char* dev = (char*)dev_base + ((size_t)b * dev_cavity_stride + (size_t)k * dev_plane_stride) * s->esz;
+            if (to_device) {
+                if (i >= 2) CK(cudaStreamWaitEvent(cs, s->ev_slot_free[slot], 0));      // its last transpose has read it
+                CK(cudaMemcpyAsync(lin, h, pbytes, cudaMemcpyHostToDevice, cs));
+                CK(cudaEventRecord(s->ev_slot_full[slot], cs));
+                CK(cudaStreamWaitEvent(st, s->ev_slot_full[slot], 0));
+                launch_transpose(s, true, dev, lin, 1, dev_plane_stride, dev_row0, st);
+                CK(cudaEventRecord(s->ev_slot_free[slot], st));
+            } else {
+                if (i >= 2) CK(cudaStreamWaitEvent(st, s->ev_slot_free[slot], 0));      // its last copy out has left
+                launch_transpose(s, false, dev, lin, 1, dev_plane_stride, dev_row0, st);
+                CK(cudaEventRecord(s->ev_slot_full[slot], st));
+                CK(cudaStreamWaitEvent(cs, s->ev_slot_full[slot], 0));
+                CK(cudaMemcpyAsync(h, lin, pbytes, cudaMemcpyDeviceToHost, cs));
+                CK(cudaEventRecord(s->ev_slot_free[slot], cs));
+            }
+            CK(cudaGetLastError());
+        }
+    }
+    CK(cudaStreamSynchronize(cs));
+    CK(cudaStreamSynchronize(st));
     return LBM_OK;
 }
 
@@ -1162,6 +1213,29 @@ int lbm_get_macros_current(lbm_handle_t s, void* rho, void* u, int on_device, vo
     rc = launch_pass(s, s->f[s->cur], s->f[s->cur ^ 1], 0, s->nyl, 1, !s->pre, true, MODE_MACROS, st);
     if (rc) return rc;
     return macros_out(s, rho, u, on_device, st);
+}
+
+int lbm_get_feq(lbm_handle_t s, void* feq, int on_device, void* stream) {
+    if (!s || !feq) return fail(LBM_EINVAL, "NULL argument");
+    int rc = set_device(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // equilibrium of the stored rho, u in the device layout of the macro planes, then the usual layout change
+    const long long n = (long long)s->cfg.batch * s->mplane;
+    if (!s->scratch) CK(cudaMalloc(&s->scratch, s->state_bytes));            // >= 9 macro planes per cavity
+    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    for (int b = 0; b < s->cfg.batch; ++b) {
+        const size_t mo = (size_t)b * s->mplane * s->esz;
+        char* out = (char*)s->scratch + 9 * mo;
+        const int nb = (int)((s->mplane + 255) / 256 < 148 * 16 ? (s->mplane + 255) / 256 : 148 * 16);
+        if (s->esz == 8) lbm_equ_kernel<double><<<nb, 256, 0, st>>>((const double*)((char*)s->rho + mo), (const double*)((char*)s->ux + mo), (const double*)((char*)s->uy + mo), (double*)out, s->mplane);
+        else lbm_equ_kernel<float><<<nb, 256, 0, st>>>((const float*)((char*)s->rho + mo), (const float*)((char*)s->ux + mo), (const float*)((char*)s->uy + mo), (float*)out, s->mplane);
+        s->launches++;
+    }
+    (void)blocks;
+    CK(cudaGetLastError());
+    const size_t fcav = (size_t)9 * s->cfg.nx * s->nyl * s->esz;
+    return move_planes(s, feq, fcav, on_device != 0, false, s->cfg.batch, 9, s->scratch, s->mplane, 9 * s->mplane, 0, st);
 }
 
 int lbm_equilibrium(int dtype, int64_t n, const void* rho, const void* ux, const void* uy, void* feq, int on_device,

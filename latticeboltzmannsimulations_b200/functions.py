@@ -13,6 +13,11 @@ calls ``equ`` once (``:210``), ``set_omega`` once (``:232``) and ``allfunc`` eve
   other OpenMP iterations have not written yet (data race), so they cannot be reproduced
   deterministically; interior nodes, rho, u and feq agree with the compiled reference to 2.2e-16.
 * ``set_omega`` keeps module-global state exactly like the reference (not re-entrant).
+* The time loop of ``MRT_cython.py:453`` hands back the ``fin`` it just received.  To let that call skip the upload --
+  the populations are still on the device -- the returned ``fin`` is marked READ-ONLY: passed back unchanged (same
+  object) it is recognised and not copied up again; code that wants to modify it must ``fin = fin.copy()`` first, which
+  is then uploaded like any other array (an in-place write raises instead of silently desynchronising the device).
+  ``feq`` is evaluated on the device from the step's own ``rho, u`` (no round trip of the moments).
 
 ``sumf``, ``ucprod`` and ``copyfunc`` are not on the live path (only in commented-out code of ``MRT_cython.py``);
 they are provided as thin NumPy one-liners for import compatibility.
@@ -20,6 +25,7 @@ they are provided as thin NumPy one-liners for import compatibility.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -32,6 +38,7 @@ _Re = 0.0
 _ysize = 0
 _solver = None
 _solver_key = None
+_resident = None      # weakref to the fin array returned last: its populations are still on the device
 
 c = np.array([[0, 0], [1, 0], [0, 1], [-1, 0], [0, -1], [1, 1], [-1, 1], [-1, -1], [1, -1]])   # functions.pyx:9
 
@@ -69,13 +76,14 @@ def equ(rho, ux, uy):
 
 
 def _get_solver(nx, ny):
-    global _solver, _solver_key
+    global _solver, _solver_key, _resident
     key = (nx, ny)
     if _solver is None or _solver_key != key:
         if _solver is not None:
             _solver.close()
         _solver = CavitySolver(nx, ny, 1, "float64", "SRT")
         _solver_key = key
+        _resident = None
     return _solver
 
 
@@ -87,15 +95,27 @@ def allfunc(rho, u, fin, feq):
     feq = _need_f64("feq", feq, 3)
     if omega == 0.0:
         raise RuntimeError("set_omega(uLB, Re, ysize) must be called before allfunc (functions.pyx:38)")
+    global _resident
     nx, ny = fin.shape[1], fin.shape[2]
     s = _get_solver(nx, ny)
     s.set_rates(uLatBo, omega, omega_minus=omega)
-    s.upload_f(fin)
+    # the array this function returned last, passed back untouched (it is read-only): its populations are on the device
+    if not (_resident is not None and _resident() is fin and not fin.flags.writeable):
+        s.upload_f(fin)
     s.step(1, write_macros=True)
-    rho_new, u_new = s.macros()
-    u[...] = u_new                                   # mutated in place (functions.pyx:73-81)
-    feq[...] = equ(rho_new, u_new[0], u_new[1])      # mutated in place (functions.pyx:88)
-    return rho_new, u, s.download_f(), feq
+    rho_new = np.empty((nx, ny))
+    if u.flags.c_contiguous:
+        s.macros(rho_out=rho_new, u_out=u)           # u mutated in place (functions.pyx:73-81)
+    else:
+        u[...] = s.macros(rho_out=rho_new)[1]
+    if feq.flags.c_contiguous:
+        s.feq(out=feq)                               # mutated in place (functions.pyx:88)
+    else:
+        feq[...] = s.feq()
+    fin_new = s.download_f()
+    fin_new.setflags(write=False)
+    _resident = weakref.ref(fin_new)
+    return rho_new, u, fin_new, feq
 
 
 def sumf(fin):                       # functions.pyx:32-33

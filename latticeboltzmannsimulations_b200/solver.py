@@ -213,6 +213,16 @@ class CavitySolver:
         _capi.check(fn(self._h, rp, up, d1, C.c_void_p(stream)))
         return rho_out, u_out
 
+    def feq(self, out=None, stream: int = 0):
+        """Equilibrium of the stored (lagged) ``rho, u``: ``feq[9, nx, ny]`` as ``functions.allfunc`` returns it."""
+        if out is None:
+            out = np.empty(self._fshape(), dtype=self.np_dtype)
+        ptr, on_dev, keep = self._host_arg(out, self._fshape())
+        if keep is not out and not on_dev:
+            raise ValueError("out must be C-contiguous")
+        _capi.check(self._lib.lbm_get_feq(self._h, ptr, on_dev, C.c_void_p(stream)))
+        return out
+
     def mean_u(self, stream: int = 0) -> np.ndarray:
         """Per-cavity ``np.mean(u)`` of the stored velocity field, reduced on the device (MRT_GPU_datagen.py:729)."""
         out = (C.c_double * self.batch)()

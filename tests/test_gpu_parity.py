@@ -241,6 +241,39 @@ def test_functions_shim_matches_oracle_and_compiled_reference():
     assert_close((rho, u, fin), want, "float64", uLB)
 
 
+def test_functions_shim_time_loop_keeps_the_state_on_the_device():
+    """The loop of MRT_cython.py:453 -- rho, u, fin, feq = allfunc(rho, u, fin, feq) -- over the shim: the returned fin
+    is read-only and recognised when it is passed back, so no call after the first uploads anything; the result equals a
+    continuous device-resident run bit for bit, a modified copy is uploaded like any array, an in-place write raises."""
+    import latticeboltzmannsimulations_b200 as L
+    import latticeboltzmannsimulations_b200.functions as F
+    nx, ny, Re, n = 40, 28, 200, 12
+    vel = np.zeros((2, nx, ny)); vel[0, :, 0] = 0.08
+    fin = F.equ(np.ones((nx, ny)), vel[0], vel[1])
+    F.set_omega(0.08, Re, ny)
+    rho = np.sum(fin, axis=0); u = np.zeros((2, nx, ny)); feq = fin.copy()
+    uploads = []
+    orig = L.CavitySolver.upload_f
+    L.CavitySolver.upload_f = lambda self, f, stream=0: (uploads.append(1), orig(self, f, stream))[1]
+    try:
+        for _ in range(n):
+            rho, u, fin, feq = F.allfunc(rho, u, fin, feq)
+        assert len(uploads) == 1 and not fin.flags.writeable
+        with pytest.raises(ValueError):
+            fin[0, 0, 0] = 1.0
+        with L.CavitySolver(nx, ny, 1, "float64", "SRT") as s:
+            s.set_rates(0.08, F.omega, omega_minus=F.omega)
+            s.init_equilibrium(); s.step(n)
+            r1, u1 = s.macros(); f1 = s.download_f(); feq1 = s.feq()
+        assert np.array_equal(fin, f1) and np.array_equal(u, u1) and np.array_equal(rho, r1) and np.array_equal(feq, feq1)
+        assert np.abs(feq - F.equ(rho, u[0], u[1])).max() <= 1e-15
+        fin2 = fin.copy(); fin2[:, 5, 5] *= 1.001                     # a modified copy: a new array, uploaded again
+        F.allfunc(rho, u, fin2, feq)
+        assert len(uploads) == 2
+    finally:
+        L.CavitySolver.upload_f = orig
+
+
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 def test_full_size_properties_4096(dtype):
     """BASELINE config 3 size (4096^2, Re 5000): size-independent properties instead of an oracle run --
