@@ -378,26 +378,22 @@ static bool fused2_capable(const lbm_solver* s) { return two_step_kind(s) != TWO
 static bool fused2_usable(const lbm_solver* s) { return fused2_capable(s) && s->nyl == s->cfg.ny; }
 
 // Rows per segment of the sliding-window kernel: 4m - 2 (m iterations of four rows cover the segment and its two halo
-// rows exactly).  Short segments pay their start-up (two halo rows, an empty pipeline) more often, long ones leave a
-// long under-occupied tail at the end of the launch; measured optima (4096^2: 46 fp64 / 30 fp32) follow
-// 2 sqrt(rows per resident CTA slot) -- up to about 48: wide / tall cavities do not want taller segments (32768 x 4096
-// fp64: 89 041 MLUPS at 46, 84 254 at 162, 81 683 at 254; tools/wide_sweep.py).  Around that height pick the one whose
-// CTA count fills whole waves best.
+// rows exactly).  Short segments pay their start-up (two halo rows, an empty pipeline) more often, tall ones leave fewer,
+// longer-lived CTAs (a long under-occupied tail; wide cavities lose 6 - 8 % at 160 - 250 rows).  The optimum is flat
+// between 22 and 38 rows on every shape measured (tools/h_sweep_fine.py: 4096^2 fp64 88 127 MLUPS at 30, 87 374 at 22,
+// 85 398 at 46; 32768 x 4096 fp64 90 797 at 26, fp32 179 971 at 38; 32 x 384^2 fp64 75 868 at 26), so pick among
+// 22 / 26 / 30 / 34 the height whose CTA count fills whole waves of 3 CTAs per SM best, weighted by rows kept / computed.
 static int slide_seg_h(const lbm_solver* s) {
     if (s->slide_h > 0) return s->slide_h;
     const int tx = 512 / s->esz;
     const long long nsx = (s->cfg.nx + tx - 1) / tx;
     const long long slots = 3LL * s->num_sms;
-    const double rows_per_slot = (double)nsx * s->nyl * s->cfg.batch / (double)slots;
-    double h0 = 2.0 * sqrt(rows_per_slot);
-    h0 = h0 < 14.0 ? 14.0 : (h0 > 48.0 ? 48.0 : h0);
-    int best = 14;
+    int best = 30;
     double best_eff = -1.0;
-    for (int h = 14; h <= 254; h += 4) {
-        if (h < 0.75 * h0 - 2 || h > 1.35 * h0 + 2) continue;
+    for (int h = 22; h <= 34; h += 4) {
         const long long items = nsx * ((s->nyl + h - 1) / h) * s->cfg.batch;
         const long long waves = (items + slots - 1) / slots;
-        const double eff = (double)items / (double)(waves * slots) * h / (h + 8.0);
+        const double eff = (double)items / (double)(waves * slots) * h / (h + 3.0);
         if (eff > best_eff + 1e-9) { best_eff = eff; best = h; }
     }
     return best;

@@ -61,11 +61,11 @@ __device__ __forceinline__ void slide_mbar_wait(unsigned bar, unsigned parity) {
         "{\n"
         ".reg .pred p;\n"
         "SLIDE_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra SLIDE_DONE;\n"
         "bra SLIDE_WAIT;\n"
         "SLIDE_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity)
+        "}\n" ::"r"(bar), "r"(parity), "r"(2000u)     /* suspend-time hint (ns): sleep in hardware instead of spinning */
         : "memory");
 }
 // one row global -> shared through the bulk copy engine; bytes and both addresses are multiples of 16
@@ -157,13 +157,17 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
     }
     __syncthreads();
 
-    // copy assignment, fixed for the whole segment: thread t < 9 R stages row j = t & 3 of population k = t >> 2
-    const int ck = tid >> 2, cj = tid & 3;
+    // copy assignment, fixed for the whole segment: the first R lanes of warp k stage rows j = 0 .. R-1 of population k
+    // (nine warps, nine populations).  A bulk copy is issued by one elected lane at a time, so spreading the 9 R copies
+    // of a stage over all warps keeps the issue off any single warp's critical path.
+    static_assert(NT == 9 * 32, "one warp per population");
+    const int ck = tid >> 5, cj = tid & 31;
+    const bool copier = cj < R;
     const int cdy = (ck == 2 || ck == 5 || ck == 6) ? 1 : ((ck == 4 || ck == 7 || ck == 8) ? -1 : 0);
 
     // ---- stage the source rows of the iteration whose first sub-step-1 row is s into buffer `buf` -----------------
     auto issue = [&](int s, int buf) {
-        if (s <= yb && tid < Cfg::COPIERS) {
+        if (s <= yb && copier) {
             const unsigned bar = bar_full + 8 * buf;
             // interior block: rows s-1 .. s+R all exist in the main buffer (no wall row, no ghost row beyond)
             const int gy0 = a.y0 + s;
