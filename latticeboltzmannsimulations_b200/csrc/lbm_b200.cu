@@ -45,7 +45,7 @@ static int fail(int code, const std::string& msg) {
                         std::string(#call) + ": " + cudaGetErrorString(e__));                            \
     } while (0)
 
-// Where temporal blocking pays (tools/small_grid.py, tools/fused2_check.py, fp64): large cavities with 64x8 tiles
+// Where the shared-memory tiles pay (round-1 sweeps, fp64; tools/size_sweep2.py): large cavities with 64x8 tiles
 // (1024^2: 45 807 -> 63 586 MLUPS, 4096^2: 47 558 -> 74 393); launch-latency-bound small cavities with 32x8 tiles, so
 // that one wave still covers all SMs (384^2: 3.46 -> 2.98 us/step, 128^2: 2.11 -> 1.97).  In between (640^2:
 // 6.23 vs 6.65 us/step) neither tile shape fills the machine well and the one-step kernel stays.
@@ -100,7 +100,7 @@ struct lbm_solver {
     int num_sms = 148;
     int tma_variant = 0;       // index into the compiled (TY, STAGES) configurations
     int tma_ctas_per_sm = 1;
-    // nodes per thread of the ldg family (1 = scalar kernel).  Measured at 4096^2 on B200 (tools/tma_sweep.py):
+    // nodes per thread of the ldg family (1 = scalar kernel).  Measured at 4096^2 on B200 (round-1 sweep.py):
     // fp64 scalar 47 067 vs vec2 45 905 MLUPS; fp32 scalar 87 132, vec2 88 321, vec4 91 055 MLUPS.
     int vec_f64 = 1, vec_f32 = 4;
     // CUDA graphs of the steady step loop: graph[p] = 2*GRAPH_PAIRS launches starting with buffer p as source
@@ -390,7 +390,8 @@ static int slide_seg_h(const lbm_solver* s) {
     const long long slots = 3LL * s->num_sms;
     int best = 30;
     double best_eff = -1.0;
-    for (int h = 22; h <= 34; h += 4) {
+    // (14 and 18 only ever win where the launch has few CTAs: 1024^2 fp64 64 372 MLUPS at 14, 61 888 at 22)
+    for (int h = 14; h <= 34; h += 4) {
         const long long items = nsx * ((s->nyl + h - 1) / h) * s->cfg.batch;
         const long long waves = (items + slots - 1) / slots;
         const double eff = (double)items / (double)(waves * slots) * h / (h + 3.0);
@@ -399,7 +400,7 @@ static int slide_seg_h(const lbm_solver* s) {
     return best;
 }
 
-// Tile-shape variant of the two-step kernel.  Defaults from tools/fused2_sweep.py at 4096^2: fp64 64x8 tiles at
+// Tile-shape variant of the two-step kernel.  Defaults from the round-1 tile sweep at 4096^2: fp64 64x8 tiles at
 // 4 CTAs/SM, fp32 32x16; cavities small enough to be launch-latency-bound take 32x8 tiles so that one wave still
 // covers all SMs (384^2 -> 576 CTAs).
 static int fused2_variant(const lbm_solver* s) {

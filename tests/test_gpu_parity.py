@@ -305,6 +305,21 @@ def test_full_size_properties_4096(dtype):
     assert np.abs(f[:, :100, :100] - want[:, :100, :100]).max() <= tol
 
 
+@pytest.mark.parametrize("coll,turb", [("MRT", 0), ("SRT", 1)])
+def test_full_field_4096_against_the_c_oracle(coll, turb):
+    """BASELINE config 3 at its full size, every node: 4096 x 4096, 21 steps (1 one-step launch + 10 launches of the
+    sliding-window two-step kernel) against the C restatement of the oracle (itself bit-identical to the NumPy oracle),
+    fp64 to 1e-12 and fp32 to 1e-5, MRT and the reference's default SRT + Smagorinsky closure."""
+    import latticeboltzmannsimulations_b200 as L
+    n, steps = 4096, 21
+    p = O.Params(n, n, Re=5000, collision=coll, turb=turb)
+    want = O.run_fast(p, steps)
+    for dtype in ("float64", "float32"):
+        got = L.run_cavity(n, n, 5000, steps=steps, collision=coll, turb=bool(turb), dtype=dtype, return_f=True)
+        assert_close(got, want, dtype, what="4096^2 full field %s turb=%d" % (coll, turb))
+        del got
+
+
 def test_mean_u_and_freeze():
     """Device reduction == np.mean of the downloaded field; a frozen cavity stops exactly where it was frozen
     while the others continue (each still equal to its standalone run, bit for bit)."""
