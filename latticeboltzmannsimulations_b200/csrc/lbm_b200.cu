@@ -100,7 +100,7 @@ struct lbm_solver {
     int num_sms = 148;
     int tma_variant = 0;       // index into the compiled (TY, STAGES) configurations
     int tma_ctas_per_sm = 1;
-    // nodes per thread of the ldg family (1 = scalar kernel).  Measured at 4096^2 on B200 (round-1 sweep.py):
+    // nodes per thread of the ldg family (1 = scalar kernel).  Measured at 4096^2 on B200 (round-1 sweep):
     // fp64 scalar 47 067 vs vec2 45 905 MLUPS; fp32 scalar 87 132, vec2 88 321, vec4 91 055 MLUPS.
     int vec_f64 = 1, vec_f32 = 4;
     // CUDA graphs of the steady step loop: graph[p] = 2*GRAPH_PAIRS launches starting with buffer p as source
