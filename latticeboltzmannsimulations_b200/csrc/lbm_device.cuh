@@ -55,9 +55,12 @@ struct StepArgs {
 template <typename T>
 struct Rates {
     T uLB, omega, omegam, s_e, s_eps, s_q, tau0;
+    // MRT rates with the constant factors of the inverse moment transform folded in once per thread (in double):
+    // q_e = s_e / 36, q_eps = s_eps / 36, q_q = s_q / 12 -- what is left in the collision are powers of two
+    T q_e, q_eps, q_q;
     __device__ __forceinline__ explicit Rates(const CavityParams& p)
         : uLB((T)p.uLB), omega((T)p.omega), omegam((T)p.omegam), s_e((T)p.s_e), s_eps((T)p.s_eps), s_q((T)p.s_q),
-          tau0((T)p.tau0) {}
+          tau0((T)p.tau0), q_e((T)(p.s_e / 36.0)), q_eps((T)(p.s_eps / 36.0)), q_q((T)(p.s_q / 12.0)) {}
 };
 
 // Lattice weights t_k (MRT.py:144-146).
@@ -294,8 +297,10 @@ __device__ __forceinline__ void collide_trt_dev(T f[9], T drho, T rho, T ux, T u
 // rho_given: the density entering the equilibrium moments when it is not the plain sum of the populations (lid row);
 // otherwise (use_given = false) it is summed here from the partial sums the transform needs anyway -- always, so that a
 // step gives the same bits whether or not it also writes rho / u (which carry the reference-order sum).
+// q_e, q_eps, q_q: the rates pre-divided by 36, 36, 12 (Rates); with s_nu / 4 every remaining factor of M^-1 is a power
+// of two: c0 = (de - dp)/9 = 4 (de' - dp'), c_axis = (de + 2 dp)/36 = de' + 2 dp', c_diag = -(2 de + dp)/36, q/6 = 2 q'.
 template <typename T>
-__device__ __forceinline__ void collide_mrt(T f[9], bool use_given, T rho_given, T s_e, T s_eps, T s_q, T s_nu) {
+__device__ __forceinline__ void collide_mrt(T f[9], bool use_given, T rho_given, T q_e, T q_eps, T q_q, T s_nu) {
     const T p13 = f[1] + f[3], m13 = f[1] - f[3];
     const T p24 = f[2] + f[4], m24 = f[2] - f[4];
     const T s57 = f[5] + f[7], d57 = f[5] - f[7];
@@ -306,7 +311,9 @@ __device__ __forceinline__ void collide_mrt(T f[9], bool use_given, T rho_given,
     const T ab = p13 + p24;
     const T rho = use_given ? rho_given : f[0] + (ab + dg);
     const T jx = m13 + jxd, jy = m24 + jyd;
-    const T e = fm((T)-4, f[0], fm((T)2, dg, -ab));
+    // written without a single unary minus (free for scalars, one more packed instruction for f32x2): en = -e,
+    // den = -de, can = -c_axis, t = -c_diag
+    const T en = fm((T)4, f[0], fm((T)-2, dg, ab));
     const T eps = fm((T)4, f[0], fm((T)-2, ab, dg));
     const T qx = fm((T)-2, m13, jxd), qy = fm((T)-2, m24, jyd);
     const T pxx = p13 - p24;
@@ -316,26 +323,25 @@ __device__ __forceinline__ void collide_mrt(T f[9], bool use_given, T rho_given,
     const T qx_eq = jx * fm((T)3, jx2, (T)-1);
     const T qy_eq = jy * fm((T)3, jy2, (T)-1);
     const T pxx_eq = jx2 - jy2, pxy_eq = jx * jy;
-    const T de = s_e * (e - e_eq);
-    const T dp = s_eps * (eps - eps_eq);
-    const T dqx = s_q * (qx - qx_eq), dqy = s_q * (qy - qy_eq);
-    const T dxx = s_nu * (pxx - pxx_eq), dxy = s_nu * (pxy - pxy_eq);
-    const T c0 = (de - dp) * (T)(1.0 / 9.0);
-    const T cax = fm((T)2, dp, de) * (T)(1.0 / 36.0);
-    const T cdg = fm((T)2, de, dp) * (T)(-1.0 / 36.0);
-    const T ax_m = fm((T)-0.25, dxx, cax), ax_p = fm((T)0.25, dxx, cax);
-    const T dg_m = fm((T)-0.25, dxy, cdg), dg_p = fm((T)0.25, dxy, cdg);
-    const T qs = (dqx + dqy) * (T)(1.0 / 12.0), qd = (dqx - dqy) * (T)(1.0 / 12.0);
-    const T s6 = (T)(1.0 / 6.0);
-    f[0] = f[0] + c0;
-    f[1] = f[1] + fm(s6, dqx, ax_m);
-    f[3] = f[3] + fm(-s6, dqx, ax_m);
-    f[2] = f[2] + fm(s6, dqy, ax_p);
-    f[4] = f[4] + fm(-s6, dqy, ax_p);
-    f[5] = f[5] + (dg_m - qs);
-    f[6] = f[6] + (dg_p + qd);
-    f[7] = f[7] + (dg_m + qs);
-    f[8] = f[8] + (dg_p - qd);
+    const T q_nu = (T)0.25 * s_nu;
+    const T den = q_e * (en + e_eq);                                  // -s_e (e - e_eq) / 36
+    const T dp = q_eps * (eps - eps_eq);                              //  s_eps (eps - eps_eq) / 36
+    const T dqx = q_q * (qx - qx_eq), dqy = q_q * (qy - qy_eq);      //  / 12
+    const T dxx = q_nu * (pxx - pxx_eq), dxy = q_nu * (pxy - pxy_eq);  //  / 4
+    const T can = fm((T)-2, dp, den);                                 // -(de + 2 dp) / 36
+    const T t = fm((T)-2, den, dp);                                   //  (2 de + dp) / 36
+    const T am = can + dxx, ap = can - dxx;
+    const T tm = t + dxy, tp = t - dxy;
+    const T qs = dqx + dqy, qd = dqx - dqy;
+    f[0] = fm((T)-4, den + dp, f[0]);                                 // + (de - dp) / 9
+    f[1] = f[1] - fm((T)-2, dqx, am);
+    f[3] = f[3] - fm((T)2, dqx, am);
+    f[2] = f[2] - fm((T)-2, dqy, ap);
+    f[4] = f[4] - fm((T)2, dqy, ap);
+    f[5] = f[5] - (tm + qs);
+    f[7] = f[7] - (tm - qs);
+    f[6] = f[6] - (tp - qd);
+    f[8] = f[8] - (tp + qd);
 }
 
 // Smagorinsky closure of MRT_GPU.py:570-589: effective relaxation rate from the non-equilibrium momentum flux
@@ -381,7 +387,7 @@ __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left
         *pi_out = fe5 - fe6 + fe7 - fe8;
     }
     if (COLL == COLL_MRT) {
-        collide_mrt<T>(f, lid, rho, r.s_e, r.s_eps, r.s_q, om);     // off the lid the same density with or without output
+        collide_mrt<T>(f, lid, rho, r.q_e, r.q_eps, r.q_q, om);     // off the lid the same density with or without output
     } else if (is_fp32<T>::value) {
         const T drho = drho_of<T>(f, lid);
         if (COLL == COLL_SRT) collide_srt_dev<T>(f, drho, rho, ux, uy, om);
