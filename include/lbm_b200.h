@@ -98,7 +98,7 @@ int lbm_get_layout(lbm_handle_t h, lbm_layout_t* out);
  *   "slide_min_nodes"     smallest batch x nx x ny that uses it instead of the shared-memory tiles (default 2000000)
  *   "slide_h"             rows per segment of the sliding-window kernel, 0 = automatic
  *   "tile"                tile shape of the shared-memory two-step kernel, -1 = automatic
- *   "vec_f64", "vec_f32"  nodes per thread of the one-step kernels (1|2, 1|2|4)
+ *   "vec_f64", "vec_f32"  nodes per thread of the one-step kernels (1|2; 0|1|2|4 with 0 = by size, the default)
  *   "graph", "pdl"        CUDA graphs for small cavities / programmatic dependent launch (default 1, 1)
  *   "tma_variant", "tma_ctas"   tile configuration and CTAs per SM of the optional TMA engine
  * Unknown keys and out-of-range values return LBM_EINVAL.  The Python binding applies the comma-separated

@@ -102,7 +102,10 @@ struct lbm_solver {
     int tma_ctas_per_sm = 1;
     // nodes per thread of the ldg family (1 = scalar kernel).  Measured at 4096^2 on B200 (round-1 sweep):
     // fp64 scalar 47 067 vs vec2 45 905 MLUPS; fp32 scalar 87 132, vec2 88 321, vec4 91 055 MLUPS.
-    int vec_f64 = 1, vec_f32 = 4;
+    // fp32: 0 = by size (tools/vec_sweep.py, us/step V = 1 / 2 / 4: 384^2 3.08 / 3.72 / 4.05, 640^2 5.83 / 5.20 / 5.82,
+    // 1024^2 12.7 / 10.0 / 10.1, 1400^2 27.5 / 25.8 / 25.4; with the closure 640^2 6.62 / 6.52 / 8.21, 1400^2 32.9 / 35.3 /
+    // 35.2): small launches want threads, large ones fewer instructions per node
+    int vec_f64 = 1, vec_f32 = 0;
     // CUDA graphs of the steady step loop: graph[p] = 2*GRAPH_PAIRS launches starting with buffer p as source
     cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};   // index = cur * 2 + side
     cudaStream_t capture_stream = nullptr;
@@ -520,7 +523,12 @@ static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin,
         return LBM_OK;
     }
     a.row_count = row_count;
-    const int vw = s->cfg.dtype == LBM_F64 ? s->vec_f64 : s->vec_f32;
+    int vw = s->cfg.dtype == LBM_F64 ? s->vec_f64 : s->vec_f32;
+    if (vw == 0) {                                   // fp32, automatic
+        const long long nodes = (long long)s->cfg.nx * s->nyl * s->cfg.batch;
+        if (s->cfg.turb) vw = (nodes <= 200000 || nodes > 1200000) ? 1 : 2;
+        else vw = nodes <= 200000 ? 1 : (nodes <= 1200000 ? 2 : 4);
+    }
     const bool vec = mode == MODE_STEP && gather && vw > 1;
     Launch L{};
     L.st = st;
@@ -747,7 +755,7 @@ int lbm_set_tuning(lbm_handle_t s, const char* key, int64_t value) {
     else if (k == "tile") { if (v < -1 || v > 9) return fail(LBM_EINVAL, "tile must lie in [-1, 9]"); s->fused2_tile = v; }
     else if (k == "two_step_min_nodes") s->fused2_min_nodes = value;
     else if (k == "vec_f64") { if (v != 1 && v != 2) return fail(LBM_EINVAL, "vec_f64 must be 1 or 2"); s->vec_f64 = v; }
-    else if (k == "vec_f32") { if (v != 1 && v != 2 && v != 4) return fail(LBM_EINVAL, "vec_f32 must be 1, 2 or 4"); s->vec_f32 = v; }
+    else if (k == "vec_f32") { if (v != 0 && v != 1 && v != 2 && v != 4) return fail(LBM_EINVAL, "vec_f32 must be 0 (by size), 1, 2 or 4"); s->vec_f32 = v; }
     else if (k == "graph") s->use_graph = v != 0;
     else if (k == "pdl") s->use_pdl = v != 0;
     else if (k == "tma_ctas") { if (v < 1) return fail(LBM_EINVAL, "tma_ctas must be >= 1"); s->tma_ctas_per_sm = v; }
@@ -1363,6 +1371,10 @@ int lbm_set_active(lbm_handle_t s, const int32_t* active, void* stream) {
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = s->cfg.batch;
+    if (s->active && s->conv_past) {   // lbm_converge_check may have retired cavities on the device since the last read-back
+        CK(cudaMemcpyAsync(s->active_host.data(), s->active, sizeof(int) * nb, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     for (int b = 0; b < nb; ++b)       // validate everything before touching any state
         if (s->active && !s->active_host[b] && active[b]) return fail(LBM_ESTATE, "a frozen cavity cannot be re-activated");
     if (!s->active) {
