@@ -96,6 +96,12 @@ __device__ __forceinline__ f32x2 operator-(f32x2 a, f32x2 b) { return f32x2(__ff
 __device__ __forceinline__ f32x2 operator-(f32x2 a) { return f32x2(__fmul2_rn(a.v, make_float2(-1.0f, -1.0f))); }
 __device__ __forceinline__ f32x2 operator/(f32x2 a, f32x2 b) { return f32x2(a.v.x / b.v.x, a.v.y / b.v.y); }
 __device__ __forceinline__ f32x2 fm(f32x2 a, f32x2 b, f32x2 c) { return f32x2(__ffma2_rn(a.v, b.v, c.v)); }
+// CAUTION (ptxas 12.9, seen in SASS): a packed product with a single use that feeds a packed ADDITION is contracted
+// into one FFMA2 although both PTX instructions carry .rn and the build passes --fmad false (the scalar pair is left
+// alone) -- the two halves then no longer equal the scalar code.  Subtractions (an FFMA2 with -1 here) and explicit
+// fm() are not touched.  So in code shared with f32x2: never write `product + x` with a product used only there; use
+// fm(), or arrange the expression as a difference.  tools/packed_check.cu compares the packed and the scalar node
+// arithmetic bit for bit on random states (GPU test test_packed_arithmetic_equals_scalar).
 using ::sqrt;       // keep the scalar overloads visible next to the packed ones
 using ::fabs;
 __device__ __forceinline__ f32x2 sqrt(f32x2 a) { return f32x2(sqrtf(a.v.x), sqrtf(a.v.y)); }
@@ -384,7 +390,7 @@ __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left
         const T r2 = rho * w_diag<T>();
         const T fe5 = feq_one(r2, ux + uy, usqr), fe6 = feq_one(r2, uy - ux, usqr);
         const T fe7 = feq_one(r2, -(ux + uy), usqr), fe8 = feq_one(r2, ux - uy, usqr);
-        *pi_out = fe5 - fe6 + fe7 - fe8;
+        *pi_out = (fe5 - fe6) - (fe8 - fe7);      // differences only: see the note on packed additions at f32x2
     }
     if (COLL == COLL_MRT) {
         collide_mrt<T>(f, lid, rho, r.q_e, r.q_eps, r.q_q, om);     // off the lid the same density with or without output

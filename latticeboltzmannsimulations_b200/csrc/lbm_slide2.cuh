@@ -206,6 +206,15 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
     const int ij = main_item ? tid >> 6 : (tid - Cfg::ITEMS) >> 1;                 // row within the block
     const int ilx = main_item ? NV * (tid & 63) + 1 : ((tid & 1) ? TX + 1 : 0);    // sub-step-1 column index (x0 - 1 + ilx)
     const int itx = NV * (tid & 63);                                               // sub-step-2 column (x0 + itx)
+    // the item's NV nodes all exist and none of them lies on a side wall: with an interior row the item takes the
+    // wall-free path.  Decided per item, not per block: in a wall strip only the one item per row that holds the wall
+    // node goes the general way (narrow cavities are mostly wall strips), and a block that hangs over the segment's
+    // last row or holds the lid / bottom row only sends those rows there.
+    const bool item_x_in = main_item && x0 + itx > 0 && x0 + itx + NV - 1 < a.nx - 1;
+    const int ijx = item_x_in ? ij : -(1 << 28);                   // row offset that fails every row test below
+    // local rows whose nodes are computed in this segment and lie on neither the lid nor the bottom wall
+    const int lo1 = max(1 - a.y0, ya - 1), hi1 = min(a.ny - 2 - a.y0, yb);         // sub-step 1: rows ya-1 .. yb
+    const int lo2 = max(1 - a.y0, ya), hi2 = min(a.ny - 2 - a.y0, yb - 1);         // sub-step 2: rows ya .. yb-1
 
     // one sub-step-1 node through the general (wall-aware) path: staged populations -> window
     auto s1_node = [&](const T* S, int s, int lx, T* w) {
@@ -291,12 +300,11 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
     unsigned it = 0;                                               // iteration count: parities of the barriers
     for (int s = s0; s <= yb; s += R, ++it) {
         const T* S = stg + buf * Cfg::STAGE;
-        const int gys = a.y0 + s;
         // ---- sub-step 1: rows [s, s+R) x columns [x0-1, x0+TX] -> window ----
-        // no wall node among the main items of this iteration (rows s .. s+R-1, columns x0 .. x0+TX-1), all exist
-        const bool inner1 = x0 > 0 && x0 + TX - 1 < a.nx - 1 && gys > 0 && gys + R - 1 < a.ny - 1 && s + R - 1 <= yb;
+        // this item's row is computed in this segment and is neither the lid nor the bottom row
+        const bool inner1 = s + ijx >= lo1 && s + ijx <= hi1;
         AT pi0, rp0;
-        if (TURB && main_item && inner1) {                         // Smagorinsky state t-1 of this item's nodes: plain
+        if (TURB && inner1) {                         // Smagorinsky state t-1 of this item's nodes: plain
             const long long m = (long long)(s + ij) * pitch + (x0 + itx);      // loads, in flight during the wait below
             pi0 = Item::ld(pi_in + m);
             rp0 = Item::ld(rp_in + m);
@@ -305,7 +313,7 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
         int ws = wbase + ij;
         ws = ws >= WR ? ws - WR : ws;
         T* w = win + ws * WW + ilx + WOFF;
-        if (main_item && inner1) {
+        if (inner1) {
             const T* c = S + ij * SW + ilx + (A - 1);              // first node of the item in population 0's staged rows
             AT f[9];
             f[0] = Item::ld(c);
@@ -343,9 +351,8 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
         __syncthreads();                                           // window rows [s, s+R) complete; staging buffer free
         issue(s + 2 * R, buf);
         // ---- sub-step 2: rows [s-1, s+R-1) x columns [x0, x0+TX) <- window ----
-        // no wall node among them, all inside the segment
-        const bool inner2 = x0 > 0 && x0 + TX - 1 < a.nx - 1 && gys - 1 > 0 && gys + R - 2 < a.ny - 1 && s - 1 >= ya &&
-                            s + R - 2 < yb;
+        // this item's row belongs to the segment and is neither the lid nor the bottom row
+        const bool inner2 = s - 1 + ijx >= lo2 && s - 1 + ijx <= hi2;
         if (main_item) {
             int wc = wbase + ij - 1;                               // window slot of row yl, of yl - 1 and of yl + 1
             wc = wc < 0 ? wc + WR : (wc >= WR ? wc - WR : wc);

@@ -10,7 +10,14 @@ def run(nx, ny, dt, coll, turb, steps, tuning):
         rho, u = s.macros()
         return rho, u, s.download_f()
 
-for (nx, ny, dt, coll, turb, steps) in [(777, 801, "float64", "TRT", False, 3), (777, 801, "float64", "TRT", False, 11),
+for (nx, ny, dt, coll, turb, steps) in [(150, 70, "float32", "SRT", True, 2), (150, 70, "float32", "SRT", True, 40),
+                                        (150, 70, "float32", "TRT", True, 40), (150, 70, "float32", "MRT", False, 40),
+                                        (1100, 600, "float32", "SRT", False, 2), (1100, 600, "float32", "SRT", False, 70),
+                                        (1001, 640, "float32", "MRT", False, 2), (1001, 640, "float32", "MRT", False, 70),
+                                        (200, 90, "float64", "MRT", False, 2), (200, 90, "float64", "MRT", False, 70),
+                                        (131, 77, "float32", "SRT", False, 2), (131, 77, "float32", "SRT", False, 70),
+                                        (96, 64, "float32", "MRT", True, 2), (96, 64, "float32", "MRT", True, 70),
+                                        (777, 801, "float64", "TRT", False, 3), (777, 801, "float64", "TRT", False, 11),
                                         (777, 801, "float64", "SRT", False, 11), (777, 801, "float64", "MRT", False, 11),
                                         (777, 801, "float32", "TRT", False, 11), (1000, 640, "float64", "TRT", False, 11),
                                         (930, 700, "float64", "SRT", True, 11), (1030, 610, "float32", "MRT", True, 11)]:
