@@ -97,6 +97,8 @@ int lbm_get_layout(lbm_handle_t h, lbm_layout_t* out);
  *   "slide"               0 = never use the sliding-window two-step kernel (default 1)
  *   "slide_min_nodes"     smallest batch x nx x ny that uses it instead of the shared-memory tiles (default 2000000)
  *   "slide_h"             rows per segment of the sliding-window kernel, 0 = automatic
+ *   "slide_tma"           1 (default): interior blocks of the sliding-window kernel are staged by tensor copies (one
+ *                         box per population and iteration), 0: one bulk copy per staged row
  *   "tile"                tile shape of the shared-memory two-step kernel, -1 = automatic
  *   "vec_f64", "vec_f32"  nodes per thread of the one-step kernels (1|2; 0|1|2|4 with 0 = by size, the default)
  *   "graph", "pdl"        CUDA graphs for small cavities / programmatic dependent launch (default 1, 1)

@@ -115,6 +115,9 @@ struct lbm_solver {
     int side = 0;              // which half of the double-buffered rho_lid / carry arrays is current
     int fused2_tile = -1;      // tile-shape variant of the fused kernel (-1 = per-dtype default)
     long long fused2_min_nodes = LBM_FUSED2_MIN_NODES;
+    int slide_tma = 1;         // sliding-window kernel: stage interior blocks by tensor copies (0: one bulk copy per row)
+    CUtensorMap tmap_slide[2]; // [buffer], box = staged row width x 4 rows
+    int tmap_slide_state = 0;  // 0 not made yet, 1 ready
     int use_slide = 1;         // sliding-window two-step kernel for large cavities / batches (no closure)
     int slide_h = 0;           // rows per segment, 0 = chosen from the number of work items
     long long slide_min_nodes = LBM_SLIDE_MIN_NODES;
@@ -221,6 +224,31 @@ static int make_tensor_maps(lbm_solver* s) {
         }
     }
     s->tmap_ok = true;
+    return LBM_OK;
+}
+
+// Tensor maps of both population buffers for the sliding-window kernel: all planes of all cavities stacked into one
+// 2-D tensor [batch * 9 * (nyl + 2)][pitch]; a box is the staged row width (512 B + 2 x 16 B halo) x 4 rows.
+static int make_slide_maps(lbm_solver* s) {
+    if (s->tmap_slide_state == 1) return LBM_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+        return fail(LBM_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    EncodeTiledFn encode = (EncodeTiledFn)fn;
+    cuuint64_t dims[2] = {(cuuint64_t)s->pitch, (cuuint64_t)s->cfg.batch * 9 * (cuuint64_t)(s->nyl + 2)};
+    cuuint64_t strides[1] = {(cuuint64_t)s->pitch * s->esz};
+    cuuint32_t estr[2] = {1, 1};
+    cuuint32_t box[2] = {(cuuint32_t)(512 / s->esz + 2 * (16 / s->esz)), 4};       // SlideCfg::SW x SlideCfg::R
+    for (int i = 0; i < 2; ++i) {
+        CUresult r = encode(&s->tmap_slide[i], s->esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                            2, s->f[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+            return fail(LBM_ECUDA, "cuTensorMapEncodeTiled (sliding-window kernel) failed with CUresult " + std::to_string((int)r));
+    }
+    s->tmap_slide_state = 1;
     return LBM_OK;
 }
 
@@ -475,7 +503,10 @@ static int launch_fused2_rows(lbm_solver* s, int row_begin, int row_count, bool 
     cudaError_t e;
     if (two_step_kind(s) == TWO_SLIDE) {
         a.seg_h = slide_seg_h(s);
+        a.slide_tma = s->slide_tma;
+        if (s->slide_tma) { int rc = make_slide_maps(s); if (rc) return rc; }
         Slide2Launch L{};
+        L.tmap = s->slide_tma ? &s->tmap_slide[s->cur] : nullptr;
         L.coll = s->cfg.collision == LBM_SRT ? COLL_SRT : s->cfg.collision == LBM_TRT ? COLL_TRT : COLL_MRT;
         L.turb = s->cfg.turb != 0; L.macros = macros; L.batch = s->cfg.batch; L.pdl = s->use_pdl != 0; L.st = st;
         e = s->esz == 8 ? launch_slide2_f64(a, L) : launch_slide2_f32(a, L);
@@ -750,6 +781,7 @@ int lbm_set_tuning(lbm_handle_t s, const char* key, int64_t value) {
     const int v = (int)value;
     if (k == "two_step") s->use_fused2 = v != 0;
     else if (k == "slide") s->use_slide = v != 0;
+    else if (k == "slide_tma") s->slide_tma = v != 0;
     else if (k == "slide_h") { if (v < 0 || v > 4096) return fail(LBM_EINVAL, "slide_h must lie in [0, 4096]"); s->slide_h = v; }
     else if (k == "slide_min_nodes") s->slide_min_nodes = value;
     else if (k == "tile") { if (v < -1 || v > 9) return fail(LBM_EINVAL, "tile must lie in [-1, 9]"); s->fused2_tile = v; }

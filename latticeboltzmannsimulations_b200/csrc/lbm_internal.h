@@ -1,5 +1,6 @@
 // Internal interface between the translation units of liblbm_b200.so (not part of the C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "lbm_device.cuh"
@@ -13,6 +14,7 @@ struct Slide2Launch {
     int batch;
     bool pdl;
     cudaStream_t st;
+    const CUtensorMap* tmap;   // tensor map of the source buffer, box = (staged row width) x (rows per iteration); NULL: none
 };
 cudaError_t launch_slide2_f64(const StepArgs& a, const Slide2Launch& L);
 cudaError_t launch_slide2_f32(const StepArgs& a, const Slide2Launch& L);

@@ -18,6 +18,7 @@
 // and one row above and below the segment (2 / seg_h) -- against 29 % for the 64x8 tiles of lbm_step_fused2.
 // The per-node arithmetic is node_update()/wall_rule() of lbm_device.cuh: bit-identical to two one-step launches.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "lbm_device.cuh"
@@ -69,6 +70,11 @@ __device__ __forceinline__ void slide_mbar_wait(unsigned bar, unsigned parity) {
         : "memory");
 }
 // one row global -> shared through the bulk copy engine; bytes and both addresses are multiples of 16
+// one 2-D box of the tensor map (columns c0 .., rows c1 ..) into shared memory, completing on the mbarrier
+__device__ __forceinline__ void slide_tensor(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void slide_bulk(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -107,7 +113,7 @@ template <> struct SlideItem<float> {
 };
 
 template <typename T, int COLL, bool MACROS, int MINB, bool TURB>
-__global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const StepArgs a) {
+__global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const StepArgs a, const __grid_constant__ CUtensorMap tmap) {
     using Cfg = SlideCfg<T, TURB>;
     constexpr int TX = Cfg::TX, A = Cfg::A, R = Cfg::R, SW = Cfg::SW, WW = Cfg::WW, WR = Cfg::WR, NT = Cfg::NT;
     constexpr int NV = Cfg::NV, WOFF = Cfg::WOFF;
@@ -115,7 +121,7 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
     using Item = SlideItem<T>;
     using AT = typename Item::AT;
     static_assert(R == 4, "the copy assignment below fixes the staged row per thread as (tid & 3)");
-    extern __shared__ __align__(16) unsigned char slide_smem[];
+    extern __shared__ __align__(128) unsigned char slide_smem[];
     T* stg = reinterpret_cast<T*>(slide_smem);                     // [2][9][R][SW]
     T* win = stg + 2 * Cfg::STAGE;                                 // [9][WR][WW]
     T* rl1 = win + Cfg::WINDOW;                                    // [TX + 2] lid density after sub-step 1
@@ -173,7 +179,16 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
             const int gy0 = a.y0 + s;
             const bool yin = gy0 - 1 >= 0 && gy0 + R <= a.ny - 1 && s - 1 >= -1 && s + R <= a.nyl;
             const unsigned d0 = stg_sa + (unsigned)((((buf * 9 + ck) * R + cj) * SW) * E);
-            if (xin && yin) {
+            if (a.slide_tma && yin) {
+                // one tensor copy per population: box = SW columns x R rows at (x0 - A, first source row); columns
+                // outside the stored row (wall strips) arrive as zeros and are never used
+                if (cj == 0) {
+                    slide_mbar_expect(bar, R * SW * E);
+                    slide_tensor(d0, &tmap, x0 - A, (b * 9 + ck) * (a.nyl + 2) + s + cdy + 1, bar);
+                } else {
+                    slide_mbar_arrive(bar);
+                }
+            } else if (xin && yin) {
                 slide_mbar_expect(bar, SW * E);
                 slide_bulk(d0, src + ck * P + (long long)(s + cj + cdy + 1) * pitch + (x0 - A), SW * E, bar);
             } else {

@@ -28,7 +28,8 @@ cudaError_t slide_launch_cfg(const StepArgs& a, const Slide2Launch& L) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = L.pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, a);
+    static const CUtensorMap no_map = {};
+    return cudaLaunchKernelEx(&cfg, kern, a, L.tmap ? *L.tmap : no_map);
 }
 
 template <typename T, int COLL, int MINB>

@@ -532,7 +532,7 @@ def test_tma_engine_parity(dtype):
 
 @pytest.mark.parametrize("tuning", ["vec_f64=2,vec_f32=2", "vec_f32=1", "graph=0,pdl=0", "two_step=0", "tile=0", "tile=4",
                                     "slide_min_nodes=0", "slide_min_nodes=0,slide_h=14", "slide_min_nodes=0,slide_h=37",
-                                    "slide_min_nodes=0,slide_h=126", "slide=0", "slide=0,tile=3"])
+                                    "slide_min_nodes=0,slide_h=126", "slide_min_nodes=0,slide_tma=0", "slide=0", "slide=0,tile=3"])
 def test_kernel_variants_are_bit_identical(tuning, monkeypatch):
     """Every compiled data-movement variant (scalar / 2 / 4 nodes per thread, with and without graphs and programmatic
     dependent launch, one-step kernels, shared-memory two-step tiles, the sliding-window two-step kernel at several
