@@ -95,7 +95,7 @@ int lbm_get_layout(lbm_handle_t h, lbm_layout_t* out);
  *   "two_step"            0 = one lattice step per launch only (default 1: temporal blocking where it pays)
  *   "two_step_min_nodes"  smallest batch x nx x ny that uses a two-step kernel (default 10000)
  *   "slide"               0 = never use the sliding-window two-step kernel (default 1)
- *   "slide_min_nodes"     smallest batch x nx x ny that uses it instead of the shared-memory tiles (default 2000000)
+ *   "slide_min_nodes"     smallest batch x nx x ny that uses it instead of the shared-memory tiles (default 1500000)
  *   "slide_h"             rows per segment of the sliding-window kernel, 0 = automatic
  *   "slide_tma"           1 (default): interior blocks of the sliding-window kernel are staged by tensor copies (one
  *                         box per population and iteration), 0: one bulk copy per staged row

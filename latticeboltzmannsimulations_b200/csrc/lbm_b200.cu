@@ -53,10 +53,12 @@ static int fail(int code, const std::string& msg) {
 #define LBM_FUSED2_SMALL_NODES 250000     // below: 32x8 tiles
 #define LBM_FUSED2_LARGE_NODES 600000     // from here: 64x8 (fp64) / 32x16 (fp32) tiles
 // The sliding-window two-step kernel (lbm_slide2.cuh: one CTA per column strip, bulk-copy double-buffered source rows)
-// takes over where its segments fill the machine (tools/size_sweep2.py: 1024^2 tiles 63 545 / sliding 59 332 MLUPS fp64,
-// 2048^2 70 677 / 74 571, 32 x 384^2 66 741 / 70 942; fp32 2048^2 100 744 / 125 098).  It also covers the Smagorinsky
-// closure (whole cavities) and batches with frozen cavities, which the tiles do not.
-#define LBM_SLIDE_MIN_NODES 2000000
+// takes over where its segments fill the machine and the state no longer fits L2 (tools/size_sweep2.py mid,
+// tools/h_sweep_mid.py, best segment height each: 1024^2 fp64 tiles 61 563 / sliding 60 102 MLUPS, fp32 one-step
+// 105 014 / sliding 98 324; 1280^2 fp64 64 311 / 67 018, fp32 85 838 / 107 881; 8 x 384^2 fp64 61 889 / 56 007;
+// 2048^2 fp64 69 576 / 80 187, fp32 88 467 / 135 781).  It also covers the Smagorinsky closure (whole cavities) and
+// batches with frozen cavities, which the tiles do not.
+#define LBM_SLIDE_MIN_NODES 1500000
 
 // ------------------------------------------------------------------------------------------------------------
 // solver object
@@ -408,25 +410,32 @@ static bool fused2_capable(const lbm_solver* s) { return two_step_kind(s) != TWO
 // ... and to lbm_step, which owns whole cavities only
 static bool fused2_usable(const lbm_solver* s) { return fused2_capable(s) && s->nyl == s->cfg.ny; }
 
-// Rows per segment of the sliding-window kernel: 4m - 2 (m iterations of four rows cover the segment and its two halo
-// rows exactly).  Short segments pay their start-up (two halo rows, an empty pipeline) more often, tall ones leave fewer,
-// longer-lived CTAs (a long under-occupied tail; wide cavities lose 6 - 8 % at 160 - 250 rows).  The optimum is flat
-// between 22 and 38 rows on every shape measured (tools/h_sweep_fine.py: 4096^2 fp64 88 127 MLUPS at 30, 87 374 at 22,
-// 85 398 at 46; 32768 x 4096 fp64 90 797 at 26, fp32 179 971 at 38; 32 x 384^2 fp64 75 868 at 26), so pick among
-// 22 / 26 / 30 / 34 the height whose CTA count fills whole waves of 3 CTAs per SM best, weighted by rows kept / computed.
+// Rows per segment of the sliding-window kernel: 4m + 2 (m + 1 iterations of four rows cover the segment and its two
+// halo rows exactly).  Cost model fitted to tools/h_sweep_mid.py and tools/h_sweep_fine.py (20 shapes from 1024^2 to
+// 32768 x 4096, both dtypes; worst regret of the pick against the best measured height 2 %):
+//   time ~ [(h + 2.5) / h + m(h) 2 / h] x (W + 0.5) / W
+//   (h + 2.5) / h   start-up of a segment: two halo rows and an empty pipeline
+//   W               CTAs / (3 per SM x SMs), NOT rounded up: CTAs are handed out as others finish, so what a launch
+//                   with few CTAs loses is the under-occupied tail, about half a CTA lifetime -> short segments
+//                   (1024^2 fp64: 60 102 MLUPS at 14 rows, 58 027 at 22, 49 670 at 34; fp32 98 324 at 10, 58 131 at 34)
+//   m(h) 2 / h      the halo rows are re-read by the segment below one CTA lifetime later; they come from L2 only
+//                   while what the resident CTAs stream in between (h x 512 B x 18 each) stays well inside it --
+//                   above ~80 MB the re-reads start to cost DRAM time (3072^2 fp64: 85 794 at 22, 82 889 at 34)
 static int slide_seg_h(const lbm_solver* s) {
     if (s->slide_h > 0) return s->slide_h;
     const int tx = 512 / s->esz;
     const long long nsx = (s->cfg.nx + tx - 1) / tx;
-    const long long slots = 3LL * s->num_sms;
-    int best = 30;
-    double best_eff = -1.0;
-    // (14 and 18 only ever win where the launch has few CTAs: 1024^2 fp64 64 372 MLUPS at 14, 61 888 at 22)
-    for (int h = 14; h <= 34; h += 4) {
-        const long long items = nsx * ((s->nyl + h - 1) / h) * s->cfg.batch;
-        const long long waves = (items + slots - 1) / slots;
-        const double eff = (double)items / (double)(waves * slots) * h / (h + 3.0);
-        if (eff > best_eff + 1e-9) { best_eff = eff; best = h; }
+    const double slots = 3.0 * s->num_sms;
+    int best = 26;
+    double best_cost = 1e300;
+    for (int h = s->esz == 4 ? 10 : 14; h <= 30; h += 4) {
+        const double items = (double)(nsx * ((s->nyl + h - 1) / h) * s->cfg.batch);
+        const double waves = items / slots;
+        const double streamed_mb = (items < slots ? items : slots) * h * 512.0 * 18.0 / 1e6;
+        double miss = (streamed_mb - 80.0) / 100.0;
+        miss = miss < 0.0 ? 0.0 : (miss > 1.0 ? 1.0 : miss);
+        const double cost = ((h + 2.5) / h + miss * 2.0 / h) * (waves + 0.5) / waves;
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = h; }
     }
     return best;
 }

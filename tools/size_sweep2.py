@@ -16,8 +16,11 @@ def run(nx, ny, batch, dt, coll, turb, tuning, steps):
             best = min(best, e0.elapsed_time(e1) / steps)
     return batch * nx * ny / best / 1e3, best
 
-for (nx, ny, batch) in [(128, 128, 1), (192, 192, 1), (384, 384, 1), (512, 512, 1), (640, 640, 1), (768, 768, 1), (1024, 1024, 1), (2048, 2048, 1),
-                        (384, 384, 32), (384, 384, 256), (192, 192, 64)]:
+SIZES = [(128, 128, 1), (192, 192, 1), (384, 384, 1), (512, 512, 1), (640, 640, 1), (768, 768, 1), (1024, 1024, 1), (2048, 2048, 1),
+         (384, 384, 32), (384, 384, 256), (192, 192, 64)]
+if len(sys.argv) > 1 and sys.argv[1] == "mid":       # around the sliding-window threshold
+    SIZES = [(768, 768, 1), (1024, 1024, 1), (1280, 1280, 1), (1536, 1536, 1), (2048, 2048, 1), (1024, 512, 1), (384, 384, 8), (384, 384, 16)]
+for (nx, ny, batch) in SIZES:
     steps = 4000 if nx * ny * batch < 1e6 else (1000 if nx * ny * batch < 8e6 else 200)
     for dt in ("float64", "float32"):
         out = []
