@@ -504,7 +504,9 @@ static int fused2_tile_height(const lbm_solver* s) {
 
 // Fused launch over local rows [row_begin, row_begin + row_count) (row_begin a multiple of the tile height); no
 // state change -- the caller flips cur / side once every band of the double step has been launched.
-static int launch_fused2_rows(lbm_solver* s, int row_begin, int row_count, bool macros, cudaStream_t st) {
+// Sliding-window kernel only: band_h > 0 launches the two edge bands of the strip -- rows [0, band_h) and
+// [nyl - band_h, nyl) -- as one grid of two segments.
+static int launch_fused2_rows(lbm_solver* s, int row_begin, int row_count, bool macros, cudaStream_t st, int band_h = 0) {
     if (row_count <= 0) return LBM_OK;
     StepArgs a = make_args(s, s->f[s->cur], s->f[s->cur ^ 1]);
     a.row_begin = row_begin; a.row_count = row_count;
@@ -512,6 +514,7 @@ static int launch_fused2_rows(lbm_solver* s, int row_begin, int row_count, bool 
     cudaError_t e;
     if (two_step_kind(s) == TWO_SLIDE) {
         a.seg_h = slide_seg_h(s);
+        if (band_h > 0) { a.seg_h = band_h; a.seg_stride = row_count - band_h; }
         a.slide_tma = s->slide_tma;
         if (s->slide_tma) { int rc = make_slide_maps(s); if (rc) return rc; }
         Slide2Launch L{};
@@ -1065,12 +1068,25 @@ int lbm_step2_region(lbm_handle_t s, int region, int write_macros, void* stream)
     cudaStream_t st = (cudaStream_t)stream;
     rc = sync_params(s, st);
     if (rc) return rc;
-    const int ty = fused2_tile_height(s), nyl = s->nyl;
+    const int nyl = s->nyl;
+    const bool wm = write_macros != 0;
+    if (two_step_kind(s) == TWO_SLIDE) {
+        // sliding-window kernel: segments of any height give the same bits, so the edge bands are as thin as the kernel
+        // allows (4m + 2 rows, m = 1: two iterations) and go out as ONE launch of two segments per column strip; the
+        // interior takes the rows in between with the height its own size asks for.  (With bands one interior segment
+        // tall the edge pass of a 32768 x 4096 strip took 134 us on the priority stream, 4 % of the pass.)
+        const int eb = 6;
+        const bool split = nyl >= 4 * eb;
+        if (region == LBM_REGION_ALL || (region == LBM_REGION_EDGE && !split)) return launch_fused2_rows(s, 0, nyl, wm, st);
+        if (region == LBM_REGION_EDGE) return launch_fused2_rows(s, 0, nyl, wm, st, eb);
+        if (region == LBM_REGION_INTERIOR) return split ? launch_fused2_rows(s, eb, nyl - 2 * eb, wm, st) : LBM_OK;
+        return fail(LBM_EINVAL, "bad region");
+    }
+    const int ty = fused2_tile_height(s);
     const int ntr = (nyl + ty - 1) / ty;                              // tile rows of the strip
     const int nb = (nyl % ty == 1 && ntr > 1) ? 2 : 1;                // bottom band must contain rows nyl-2 and nyl-1
     const bool split = ntr > 1 + nb;                                  // otherwise the edge bands are the whole strip
     const int bot0 = (ntr - nb) * ty;                                 // first row of the bottom band
-    const bool wm = write_macros != 0;
     if (region == LBM_REGION_ALL || (region == LBM_REGION_EDGE && !split)) return launch_fused2_rows(s, 0, nyl, wm, st);
     if (region == LBM_REGION_EDGE) {
         rc = launch_fused2_rows(s, 0, ty, wm, st);

@@ -50,6 +50,8 @@ struct StepArgs {
     int row_begin, row_stride; // local row of launch row 0 and distance between consecutive launch rows
     int row_count;             // launch rows (blockIdx.y * blockDim.y + threadIdx.y < row_count)
     int seg_h;                 // sliding-window two-step kernel: rows per segment (one CTA each)
+    int seg_stride;            //   0: segments follow each other; else exactly two segments whose first rows are this far
+                               //   apart (the two edge bands of a y-strip in one launch)
     int slide_tma;             //   1: interior blocks are staged by tensor copies (one box per population), 0: row copies
 };
 

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
     if (a.active && !a.active[b]) return;                          // frozen (converged) cavity
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TX;
-    const int ya = a.row_begin + blockIdx.y * a.seg_h;             // segment [ya, yb) of local rows
+    const int ya = a.row_begin + blockIdx.y * (a.seg_stride ? a.seg_stride : a.seg_h);   // segment [ya, yb) of local rows
     const int row_end = a.row_begin + a.row_count;
     const int yb = ya + a.seg_h < row_end ? ya + a.seg_h : row_end;
     const T* __restrict__ src = static_cast<const T*>(a.src) + (long long)b * a.cavity;

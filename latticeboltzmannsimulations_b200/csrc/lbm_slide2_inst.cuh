@@ -17,7 +17,7 @@ cudaError_t slide_launch_cfg(const StepArgs& a, const Slide2Launch& L) {
         if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM)) return e;
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    const int nseg = (a.row_count + a.seg_h - 1) / a.seg_h;
+    const int nseg = a.seg_stride ? 2 : (a.row_count + a.seg_h - 1) / a.seg_h;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((a.nx + Cfg::TX - 1) / Cfg::TX, nseg, L.batch);
     cfg.blockDim = dim3(Cfg::NT, 1, 1);
