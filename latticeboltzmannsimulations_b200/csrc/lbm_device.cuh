@@ -39,7 +39,7 @@ struct StepArgs {
     void* carry_out;           //   half of the double-buffered allocation); single-step kernels update in place
     const void* ghost2;        // fused kernel on a y-strip: [batch][top|bottom][3][pitch] second ghost rows of `src`
     void* pi_eq;               // [batch][nyl][pitch]  sum_k cx cy feq_k of the previous step (Smagorinsky only)
-    void* rho_prev;            // [batch][nyl][pitch]  rho of the previous step            (Smagorinsky only)
+    void* rho_prev;            // [batch][nyl][pitch]  1 / rho of the previous step        (Smagorinsky only)
     void* pi_eq_out;           // two-step kernels: the other half of the double-buffered Smagorinsky state (one-step
     void* rho_prev_out;        //   kernels update in place)
     const CavityParams* cav;   // [batch]
@@ -357,26 +357,29 @@ __device__ __forceinline__ void collide_mrt(T f[9], bool use_given, T rho_given,
 // Q = sum_k cx cy (f_k - feq_k^prev), with feq and rho of the PREVIOUS step (the reference reads feq_g / rho_g before
 // overwriting them) and Cs2 hard-set to 0.025 (:578; the Van-Driest lines above it are dead code).
 template <typename T>
-__device__ __forceinline__ T smagorinsky_omega(const T f[9], T pi_prev, T rho_prev, T tau0) {
+__device__ __forceinline__ T smagorinsky_omega(const T f[9], T pi_prev, T irho_prev, T tau0) {
+    // irho_prev = 1 / rho of the previous step: node_update() has that reciprocal anyway (u = j / rho) and hands it
+    // out, so the closure costs one division (the final 1 / tau, written 2 / (tau0 + sqrt(..))) instead of two
     const T product1 = f[5] - f[6] + f[7] - f[8];
     const T Qmf = product1 - pi_prev;
-    const T tau = (T)0.5 * (tau0 + sqrt(fm(tau0, tau0, ((T)(18 * 1.4142 * 0.025) * fabs(Qmf)) / rho_prev)));
-    return (T)1.0 / tau;
+    return (T)2.0 / (tau0 + sqrt(fm(tau0, tau0, ((T)(18 * 1.4142 * 0.025) * fabs(Qmf)) * irho_prev)));
 }
 
 // Everything after the gather for one node: overrides, optional macro output values, collision in place.
-// Returns rho (lid-overridden) and the output velocity through the references; with TURB also sum_k cx cy feq_k.
+// Returns rho (lid-overridden) and the output velocity through the references; with TURB also the closure's state for
+// the next step: sum_k cx cy feq_k and 1 / rho.
 template <typename T, int COLL, bool NEED_U, bool TURB = false>
 __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left, bool right, bool lid, bool bot,
-                                            T& rho_out, T& ux_out, T& uy_out, T omega_nu = (T)0, T* pi_out = nullptr) {
-    T rho = (T)0, ux = (T)0, uy = (T)0;
+                                            T& rho_out, T& ux_out, T& uy_out, T omega_nu = (T)0, T* pi_out = nullptr,
+                                            T* irho_out = nullptr) {
+    T rho = (T)0, ux = (T)0, uy = (T)0, inv = (T)0;
     // MRT without output and without closure needs neither u nor (off the lid) the reference-order density: the
     // collision sums rho from its own partial sums; rho_out is then only defined on the lid row
     constexpr bool LEAN = COLL == COLL_MRT && !NEED_U && !TURB;
     if (!LEAN) {
         T jx, jy;
         moments_ref<T>(f, rho, jx, jy);
-        const T inv = (T)1 / rho;                  // u = j / rho as one reciprocal and two multiplications
+        inv = (T)1 / rho;                          // u = j / rho as one reciprocal and two multiplications
         ux = jx * inv;
         uy = jy * inv;
     }
@@ -385,15 +388,16 @@ __device__ __forceinline__ void node_update(T f[9], const Rates<T>& r, bool left
         rho = rho_lid_formula<T>(f);
         ux = r.uLB;
         uy = (T)0;
+        if (TURB) inv = (T)1 / rho;
     }
     rho_out = rho; ux_out = ux; uy_out = uy;
     const T om = TURB ? omega_nu : r.omega;
-    if (TURB) {       // sum_k cx cy feq_k = feq5 - feq6 + feq7 - feq8, the next step's pi_prev
-        const T usqr = fm(ux, ux, uy * uy);
-        const T r2 = rho * w_diag<T>();
-        const T fe5 = feq_one(r2, ux + uy, usqr), fe6 = feq_one(r2, uy - ux, usqr);
-        const T fe7 = feq_one(r2, -(ux + uy), usqr), fe8 = feq_one(r2, ux - uy, usqr);
-        *pi_out = (fe5 - fe6) - (fe8 - fe7);      // differences only: see the note on packed additions at f32x2
+    if (TURB) {
+        // the next step's pi_prev = sum_k cx cy feq_k = feq5 - feq6 + feq7 - feq8 (MRT_GPU.py:575 on the stored feq).  For
+        // the reference's equilibrium the constant and linear terms cancel and the squares leave 4.5/36 * 8 ux uy: the sum
+        // IS rho ux uy -- two multiplications instead of four equilibria, and without their cancellation error
+        *pi_out = rho * ux * uy;
+        *irho_out = inv;
     }
     if (COLL == COLL_MRT) {
         collide_mrt<T>(f, lid, rho, r.q_e, r.q_eps, r.q_q, om);     // off the lid the same density with or without output

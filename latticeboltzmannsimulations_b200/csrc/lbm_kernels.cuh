@@ -106,10 +106,10 @@ __global__ void __launch_bounds__(256) lbm_step_ldg(const StepArgs a) {
             T* pi = static_cast<T*>(a.pi_eq) + m;
             T* rp = static_cast<T*>(a.rho_prev) + m;
             const T om = smagorinsky_omega<T>(f, *pi, *rp, r.tau0);
-            T pi_new;
-            node_update<T, COLL, MACROS, true>(f, r, left, right, lid, bot, rho, ux, uy, om, &pi_new);
+            T pi_new, irho_new;
+            node_update<T, COLL, MACROS, true>(f, r, left, right, lid, bot, rho, ux, uy, om, &pi_new, &irho_new);
             *pi = pi_new;
-            *rp = rho;
+            *rp = irho_new;
         } else {
             node_update<T, COLL, MACROS>(f, r, left, right, lid, bot, rho, ux, uy);
         }
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) lbm_step_vec(const StepArgs a) {
         f[v][7] = v == V - 1 ? h7 : v7[v + 1];
     }
     T rho[V], ux[V], uy[V];
-    T pi_old[V], rp_old[V], pi_new[V];
+    T pi_old[V], rp_old[V], pi_new[V], rp_new[V];
     if (TURB) {   // previous-step sum cx cy feq and rho of these nodes (pitch padding keeps the vector access in bounds)
         const long long m = (long long)b * a.mplane + (long long)yl * a.pitch + x;
         gload<T, V>(static_cast<const T*>(a.pi_eq) + m, pi_old);
@@ -239,10 +239,10 @@ __global__ void __launch_bounds__(256) lbm_step_vec(const StepArgs a) {
             wall_rule<T>(f[v], left, right, lid, bot, rl, r.uLB, stale);
             if (slot >= 0) carry[slot] = corner_value<T>(f[v], slot);
         }
-        if (TURB) pi_new[v] = (T)0;
+        if (TURB) { pi_new[v] = (T)0; rp_new[v] = (T)0; }
         if (TURB) {
             const T om = smagorinsky_omega<T>(f[v], pi_old[v], rp_old[v], r.tau0);
-            node_update<T, COLL, MACROS, true>(f[v], r, left, right, lid, bot, rho[v], ux[v], uy[v], om, &pi_new[v]);
+            node_update<T, COLL, MACROS, true>(f[v], r, left, right, lid, bot, rho[v], ux[v], uy[v], om, &pi_new[v], &rp_new[v]);
         } else {
             node_update<T, COLL, MACROS>(f[v], r, left, right, lid, bot, rho[v], ux[v], uy[v]);
         }
@@ -251,11 +251,11 @@ __global__ void __launch_bounds__(256) lbm_step_vec(const StepArgs a) {
         const long long m = (long long)b * a.mplane + (long long)yl * a.pitch + x;
         if (x + V <= a.nx) {
             gstore<T, V>(static_cast<T*>(a.pi_eq) + m, pi_new);
-            gstore<T, V>(static_cast<T*>(a.rho_prev) + m, rho);
+            gstore<T, V>(static_cast<T*>(a.rho_prev) + m, rp_new);
         } else {
 #pragma unroll
             for (int v = 0; v < V; ++v)
-                if (x + v < a.nx) { static_cast<T*>(a.pi_eq)[m + v] = pi_new[v]; static_cast<T*>(a.rho_prev)[m + v] = rho[v]; }
+                if (x + v < a.nx) { static_cast<T*>(a.pi_eq)[m + v] = pi_new[v]; static_cast<T*>(a.rho_prev)[m + v] = rp_new[v]; }
         }
     }
     if (lid) {

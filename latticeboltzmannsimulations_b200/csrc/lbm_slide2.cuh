@@ -253,11 +253,11 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
         T rho, ux, uy;
         if (TURB) {
             const long long m = (long long)q * pitch + x;
-            T pi1;
+            T pi1, ir1;
             const T om = smagorinsky_omega<T>(f, pi_in[m], rp_in[m], rt.tau0);
-            node_update<T, COLL, false, true>(f, rt, left, right, lid, bot, rho, ux, uy, om, &pi1);
+            node_update<T, COLL, false, true>(f, rt, left, right, lid, bot, rho, ux, uy, om, &pi1, &ir1);
             w[9 * WR * WW] = pi1;
-            w[10 * WR * WW] = rho;
+            w[10 * WR * WW] = ir1;
         } else {
             node_update<T, COLL, false>(f, rt, left, right, lid, bot, rho, ux, uy);
         }
@@ -285,12 +285,12 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
             slide_walls<T>(f, left, right, lid, bot, lid ? rl1[tx + 1] : (T)1, rt.uLB, c1, static_cast<T*>(a.carry_out) + b * 4);
         T rho, ux, uy;
         if (TURB) {
-            T pi2;
+            T pi2, ir2;
             const T om = smagorinsky_omega<T>(f, pc[9 * WR * WW], pc[10 * WR * WW], rt.tau0);
-            node_update<T, COLL, MACROS, true>(f, rt, left, right, lid, bot, rho, ux, uy, om, &pi2);
+            node_update<T, COLL, MACROS, true>(f, rt, left, right, lid, bot, rho, ux, uy, om, &pi2, &ir2);
             const long long mt = (long long)yl * pitch + x;
             pi_out[mt] = pi2;
-            rp_out[mt] = rho;
+            rp_out[mt] = ir2;
         } else {
             node_update<T, COLL, MACROS>(f, rt, left, right, lid, bot, rho, ux, uy);
         }
@@ -340,10 +340,10 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
             f[6] = Item::ldx(c + 6 * R * SW, 1);
             f[7] = Item::ldx(c + 7 * R * SW, 1);
             f[8] = Item::ldx(c + 8 * R * SW, -1);
-            AT rho, ux, uy, pi1;
+            AT rho, ux, uy, pi1, ir1;
             if (TURB) {
                 const AT om = smagorinsky_omega<AT>(f, pi0, rp0, rta.tau0);
-                node_update<AT, COLL, false, true>(f, rta, false, false, false, false, rho, ux, uy, om, &pi1);
+                node_update<AT, COLL, false, true>(f, rta, false, false, false, false, rho, ux, uy, om, &pi1, &ir1);
             } else {
                 node_update<AT, COLL, false>(f, rta, false, false, false, false, rho, ux, uy);
             }
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
             for (int k = 0; k < 9; ++k) Item::st(w + k * WR * WW, f[k]);
             if (TURB) {
                 Item::st(w + 9 * WR * WW, pi1);
-                Item::st(w + 10 * WR * WW, rho);
+                Item::st(w + 10 * WR * WW, ir1);
             }
         } else {
             slide_mbar_wait(bar_free, it & 1);
@@ -392,12 +392,12 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
                 AT rho, ux, uy;
                 const int yl = s - 1 + ij;
                 if (TURB) {
-                    AT pi2;
+                    AT pi2, ir2;
                     const AT om = smagorinsky_omega<AT>(f, Item::ld(pc + 9 * WR * WW), Item::ld(pc + 10 * WR * WW), rta.tau0);
-                    node_update<AT, COLL, MACROS, true>(f, rta, false, false, false, false, rho, ux, uy, om, &pi2);
+                    node_update<AT, COLL, MACROS, true>(f, rta, false, false, false, false, rho, ux, uy, om, &pi2, &ir2);
                     const long long mt = (long long)yl * pitch + (x0 + itx);
                     Item::st(pi_out + mt, pi2);
-                    Item::st(rp_out + mt, rho);
+                    Item::st(rp_out + mt, ir2);
                 } else {
                     node_update<AT, COLL, MACROS>(f, rta, false, false, false, false, rho, ux, uy);
                 }

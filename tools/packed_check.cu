@@ -36,23 +36,23 @@ __device__ void one(int combo, const CavityParams& cp, const float fa[9], const 
     float A[9], B[9];
     f32x2 P[9];
     for (int k = 0; k < 9; ++k) { A[k] = fa[k]; B[k] = fb[k]; P[k] = f32x2(fa[k], fb[k]); }
-    float ra, uxa, uya, rb, uxb, uyb, p1a = 0, p1b = 0;
-    f32x2 rp_, uxp, uyp, p1p(0.0f);
+    float ra, uxa, uya, rb, uxb, uyb, p1a = 0, p1b = 0, ia = 0, ib = 0;
+    f32x2 rp_, uxp, uyp, p1p(0.0f), ip(0.0f);
     const float oma = TURB ? smagorinsky_omega<float>(A, pia, rpa, rt.tau0) : 0.0f;
     const float omb = TURB ? smagorinsky_omega<float>(B, pib, rpb, rt.tau0) : 0.0f;
     const f32x2 omp = TURB ? smagorinsky_omega<f32x2>(P, f32x2(pia, pib), f32x2(rpa, rpb), rta.tau0) : f32x2(0.0f);
-    node_update<float, COLL, NEED_U, TURB>(A, rt, false, false, false, false, ra, uxa, uya, oma, &p1a);
-    node_update<float, COLL, NEED_U, TURB>(B, rt, false, false, false, false, rb, uxb, uyb, omb, &p1b);
-    node_update<f32x2, COLL, NEED_U, TURB>(P, rta, false, false, false, false, rp_, uxp, uyp, omp, &p1p);
+    node_update<float, COLL, NEED_U, TURB>(A, rt, false, false, false, false, ra, uxa, uya, oma, &p1a, &ia);
+    node_update<float, COLL, NEED_U, TURB>(B, rt, false, false, false, false, rb, uxb, uyb, omb, &p1b, &ib);
+    node_update<f32x2, COLL, NEED_U, TURB>(P, rta, false, false, false, false, rp_, uxp, uyp, omp, &p1p, &ip);
     constexpr bool LEAN = COLL == COLL_MRT && !NEED_U && !TURB;
     float va[13], vb[13];
     for (int k = 0; k < 9; ++k) { va[k] = A[k]; vb[k] = P[k].v.x; }
     va[9] = LEAN ? 0 : ra; vb[9] = LEAN ? 0 : rp_.v.x; va[10] = LEAN ? 0 : uxa; vb[10] = LEAN ? 0 : uxp.v.x;
-    va[11] = TURB ? p1a : 0; vb[11] = TURB ? p1p.v.x : 0; va[12] = oma; vb[12] = omp.v.x;
+    va[11] = TURB ? p1a + ia : 0; vb[11] = TURB ? p1p.v.x + ip.v.x : 0; va[12] = oma; vb[12] = omp.v.x;
     float wa[13], wb[13];
     for (int k = 0; k < 9; ++k) { wa[k] = B[k]; wb[k] = P[k].v.y; }
     wa[9] = LEAN ? 0 : rb; wb[9] = LEAN ? 0 : rp_.v.y; wa[10] = LEAN ? 0 : uxb; wb[10] = LEAN ? 0 : uxp.v.y;
-    wa[11] = TURB ? p1b : 0; wb[11] = TURB ? p1p.v.y : 0; wa[12] = omb; wb[12] = omp.v.y;
+    wa[11] = TURB ? p1b + ib : 0; wb[11] = TURB ? p1p.v.y + ip.v.y : 0; wa[12] = omb; wb[12] = omp.v.y;
     bool ok0 = true, ok1 = true;
     for (int k = 0; k < 13; ++k) {
         ok0 = ok0 && __float_as_uint(va[k]) == __float_as_uint(vb[k]);
