@@ -218,15 +218,24 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
     // column x0 + NV (t % 64) in both sub-steps; threads ITEMS .. ITEMS + 2R - 1 own one ring node each in sub-step 1
     const bool main_item = tid < Cfg::ITEMS;
     const bool ring_item = !main_item && tid < Cfg::ITEMS + 2 * R;
-    const int ij = main_item ? tid >> 6 : (tid - Cfg::ITEMS) >> 1;                 // row within the block
-    const int ilx = main_item ? NV * (tid & 63) + 1 : ((tid & 1) ? TX + 1 : 0);    // sub-step-1 column index (x0 - 1 + ilx)
-    const int itx = NV * (tid & 63);                                               // sub-step-2 column (x0 + itx)
+    // wall lanes: the next 2R lanes of the ninth warp (idle otherwise) own the side-wall node of row j -- even lane the
+    // left wall, odd lane the right one -- if this strip holds that column.  They run the general path for it in both
+    // sub-steps next to the ring lanes, so that in rows between lid and bottom no main warp ever leaves the wall-free
+    // path: a wall item computes all its nodes as if interior and stores only those that are (without the closure;
+    // with it, wall items take the general path themselves)
+    constexpr bool WALL_LANES = !TURB;
+    const int wl = tid - (Cfg::ITEMS + 2 * R);
+    const int wall_x = (wl & 1) ? a.nx - 1 : 0;
+    const bool wall_lane = WALL_LANES && wl >= 0 && wl < 2 * R && wall_x >= x0 && wall_x < x0 + TX;
+    const int ij = main_item ? tid >> 6 : (ring_item ? (tid - Cfg::ITEMS) >> 1 : (wl >> 1) & (R - 1));    // row within the block
+    const int itx = main_item ? NV * (tid & 63) : wall_x - x0;                     // sub-step-2 column (x0 + itx)
+    const int ilx = ring_item ? ((tid & 1) ? TX + 1 : 0) : itx + 1;                // sub-step-1 column index (x0 - 1 + ilx)
     // the item's NV nodes all exist and none of them lies on a side wall: with an interior row the item takes the
-    // wall-free path.  Decided per item, not per block: in a wall strip only the one item per row that holds the wall
-    // node goes the general way (narrow cavities are mostly wall strips), and a block that hangs over the segment's
-    // last row or holds the lid / bottom row only sends those rows there.
+    // wall-free path.  Decided per item, not per block: a block that hangs over the segment's last row or holds the
+    // lid / bottom row only sends those rows the general way (narrow cavities are mostly wall strips).
     const bool item_x_in = main_item && x0 + itx > 0 && x0 + itx + NV - 1 < a.nx - 1;
-    const int ijx = item_x_in ? ij : -(1 << 28);                   // row offset that fails every row test below
+    // an item of several nodes that holds a wall column or hangs over the last column
+    const bool item_x_edge = WALL_LANES && NV > 1 && main_item && !item_x_in && x0 + itx < a.nx;
     // local rows whose nodes are computed in this segment and lie on neither the lid nor the bottom wall
     const int lo1 = max(1 - a.y0, ya - 1), hi1 = min(a.ny - 2 - a.y0, yb);         // sub-step 1: rows ya-1 .. yb
     const int lo2 = max(1 - a.y0, ya), hi2 = min(a.ny - 2 - a.y0, yb - 1);         // sub-step 2: rows ya .. yb-1
@@ -317,7 +326,8 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
         const T* S = stg + buf * Cfg::STAGE;
         // ---- sub-step 1: rows [s, s+R) x columns [x0-1, x0+TX] -> window ----
         // this item's row is computed in this segment and is neither the lid nor the bottom row
-        const bool inner1 = s + ijx >= lo1 && s + ijx <= hi1;
+        const bool rin1 = s + ij >= lo1 && s + ij <= hi1;
+        const bool inner1 = rin1 && item_x_in, edge1 = rin1 && item_x_edge;
         AT pi0, rp0;
         if (TURB && inner1) {                         // Smagorinsky state t-1 of this item's nodes: plain
             const long long m = (long long)(s + ij) * pitch + (x0 + itx);      // loads, in flight during the wait below
@@ -328,7 +338,7 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
         int ws = wbase + ij;
         ws = ws >= WR ? ws - WR : ws;
         T* w = win + ws * WW + ilx + WOFF;
-        if (inner1) {
+        if (inner1 || edge1) {
             const T* c = S + ij * SW + ilx + (A - 1);              // first node of the item in population 0's staged rows
             AT f[9];
             f[0] = Item::ld(c);
@@ -348,18 +358,31 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
                 node_update<AT, COLL, false>(f, rta, false, false, false, false, rho, ux, uy);
             }
             slide_mbar_wait(bar_free, it & 1);                     // everybody's sub-step 2 of the previous iteration has
-#pragma unroll                                                     // read the window rows overwritten now
-            for (int k = 0; k < 9; ++k) Item::st(w + k * WR * WW, f[k]);
-            if (TURB) {
-                Item::st(w + 9 * WR * WW, pi1);
-                Item::st(w + 10 * WR * WW, ir1);
+            if (inner1) {                                          // read the window rows overwritten now
+#pragma unroll
+                for (int k = 0; k < 9; ++k) Item::st(w + k * WR * WW, f[k]);
+                if (TURB) {
+                    Item::st(w + 9 * WR * WW, pi1);
+                    Item::st(w + 10 * WR * WW, ir1);
+                }
+            } else {                                               // wall item: keep the interior nodes only
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const int xv = x0 + itx + v;
+                    if (xv > 0 && xv < a.nx - 1) {
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) w[k * WR * WW + v] = Item::get(f[k], v);
+                    }
+                }
             }
         } else {
             slide_mbar_wait(bar_free, it & 1);
             if (main_item) {
+                if (!WALL_LANES || !rin1) {                        // (else: the wall lane has this item's only node)
 #pragma unroll
-                for (int v = 0; v < NV; ++v) s1_node(S, s, ilx + v, w + v);
-            } else if (ring_item) {
+                    for (int v = 0; v < NV; ++v) s1_node(S, s, ilx + v, w + v);
+                }
+            } else if (ring_item || (wall_lane && rin1)) {
                 s1_node(S, s, ilx, w);
             }
         }
@@ -367,8 +390,9 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
         issue(s + 2 * R, buf);
         // ---- sub-step 2: rows [s-1, s+R-1) x columns [x0, x0+TX) <- window ----
         // this item's row belongs to the segment and is neither the lid nor the bottom row
-        const bool inner2 = s - 1 + ijx >= lo2 && s - 1 + ijx <= hi2;
-        if (main_item) {
+        const bool rin2 = s - 1 + ij >= lo2 && s - 1 + ij <= hi2;
+        const bool inner2 = rin2 && item_x_in, edge2 = rin2 && item_x_edge;
+        if (main_item || (wall_lane && rin2)) {
             int wc = wbase + ij - 1;                               // window slot of row yl, of yl - 1 and of yl + 1
             wc = wc < 0 ? wc + WR : (wc >= WR ? wc - WR : wc);
             int wu = wc - 1;
@@ -378,7 +402,7 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
             const T* pc = win + wc * WW + itx + 1 + WOFF;
             const T* pu = win + wu * WW + itx + 1 + WOFF;
             const T* pd = win + wd * WW + itx + 1 + WOFF;
-            if (inner2) {
+            if (inner2 || edge2) {
                 AT f[9];
                 f[0] = Item::ld(pc);
                 f[1] = Item::ldx(pc + 1 * WR * WW, -1);
@@ -402,17 +426,37 @@ __global__ void __launch_bounds__(SlideCfg<T>::NT, MINB) lbm_step_slide2(const S
                     node_update<AT, COLL, MACROS>(f, rta, false, false, false, false, rho, ux, uy);
                 }
                 T* d = dst + (long long)(yl + 1) * pitch + (x0 + itx);
+                const long long m = (long long)b * a.mplane + (long long)yl * pitch + (x0 + itx);
+                if (inner2) {
 #pragma unroll
-                for (int k = 0; k < 9; ++k) Item::st(d + k * P, f[k]);
-                if (MACROS) {
-                    const long long m = (long long)b * a.mplane + (long long)yl * pitch + (x0 + itx);
-                    Item::st(static_cast<T*>(a.rho) + m, rho);
-                    Item::st(static_cast<T*>(a.ux) + m, ux);
-                    Item::st(static_cast<T*>(a.uy) + m, uy);
+                    for (int k = 0; k < 9; ++k) Item::st(d + k * P, f[k]);
+                    if (MACROS) {
+                        Item::st(static_cast<T*>(a.rho) + m, rho);
+                        Item::st(static_cast<T*>(a.ux) + m, ux);
+                        Item::st(static_cast<T*>(a.uy) + m, uy);
+                    }
+                } else {                                           // wall item: keep the interior nodes only
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const int xv = x0 + itx + v;
+                        if (xv > 0 && xv < a.nx - 1) {
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) d[k * P + v] = Item::get(f[k], v);
+                            if (MACROS) {
+                                static_cast<T*>(a.rho)[m + v] = Item::get(rho, v);
+                                static_cast<T*>(a.ux)[m + v] = Item::get(ux, v);
+                                static_cast<T*>(a.uy)[m + v] = Item::get(uy, v);
+                            }
+                        }
+                    }
+                }
+            } else if (main_item) {
+                if (!WALL_LANES || !rin2) {                        // (else: the wall lane has this item's only node)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) s2_node(s, itx + v, pc + v, pu + v, pd + v);
                 }
             } else {
-#pragma unroll
-                for (int v = 0; v < NV; ++v) s2_node(s, itx + v, pc + v, pu + v, pd + v);
+                s2_node(s, itx, pc, pu, pd);                       // wall lane
             }
         }
         slide_mbar_arrive(bar_free);                               // this thread is done reading the window
