@@ -71,9 +71,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed for " + ", ".join(failed))
     objs = [os.path.join(OBJDIR, src[:-3] + ".o") for src in SOURCES]
-    subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
-    with open(STAMP, "w") as fh:
+    # link next to the target and rename: a process that loads the library meanwhile (several ranks of one job start
+    # together) sees the old file or the new one, never a half-written one
+    tmp = "%s.%d.tmp" % (LIB, os.getpid())
+    try:
+        subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs)
+        os.replace(tmp, LIB)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+    with open(STAMP + ".tmp", "w") as fh:
         fh.write(_source_hash() + "\n")
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB
 
 

@@ -4,11 +4,13 @@
   strip boundary is a whole row).  The update of a row reads only rows y-1, y, y+1, hence exactly one
   nearest-neighbour exchange per step: across each interface the three populations that cross it
   (towards larger y: k in {4,7,8}; towards smaller y: k in {2,5,6}), ``3 * nx`` values per direction -- nine rows
-  per direction when the two-step (temporal blocking) kernel is used, which recomputes the ghost row.  Per step
-  the two edge rows of the strip are updated first on a halo stream, their crossing populations are sent straight
-  from / received straight into the population buffers (row views, no pack kernels) with grouped NCCL send/recv,
-  and the interior rows are updated concurrently on the main stream.  The reference has no multi-GPU path at all
-  (single ``cuda.Device(0)``), so there is no upstream interface to mirror here.
+  per direction when the two-step (temporal blocking) kernel is used, which recomputes the ghost row.  Per (double)
+  step the edge bands of the strip are updated first on a high-priority halo stream, the nine rows for each neighbour
+  are gathered into ONE contiguous buffer (``lbm_halo_pack``), exchanged with one grouped NCCL send + recv per
+  interface and scattered into the ghost rows (``lbm_halo_unpack``), while the interior rows are updated concurrently
+  on the main stream.  Strips of a single row (shallow plan) exchange row views of the population buffers directly.
+  The reference has no multi-GPU path at all (single ``cuda.Device(0)``), so there is no upstream
+  interface to mirror here.
 * ``datagen_sharded`` -- the Reynolds sweep of ``MRT_GPU_datagen.py:55-57``: independent cavities, rank r takes the
   cavities ``r::world``; no data-path collective (results are gathered once at the end).
 
