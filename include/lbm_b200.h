@@ -61,7 +61,8 @@ typedef struct lbm_config {
     int32_t semantics;    /* lbm_semantics */
     int32_t reserved;     /* must be 0 */
     void* ext_f[2];       /* optional caller-owned device buffers (e.g. torch tensors) for the A/B population
-                             arrays, each lbm_state_bytes() long; NULL = the library allocates */
+                             arrays, each lbm_state_bytes() long; both NULL = the library allocates
+                             (one NULL and one not, or twice the same pointer: LBM_EINVAL) */
 } lbm_config_t;
 
 /* Private device layout, for callers that move halo rows themselves (NCCL send/recv on row views). */

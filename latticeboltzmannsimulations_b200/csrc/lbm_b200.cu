@@ -647,6 +647,9 @@ static int check_cfg(const lbm_config_t* c, int* nyl_out) {
     if (c->engine < LBM_ENGINE_AUTO || c->engine > LBM_ENGINE_TMA) return fail(LBM_EINVAL, "bad engine");
     if (c->semantics != LBM_SEMANTICS_C && c->semantics != LBM_SEMANTICS_A) return fail(LBM_EINVAL, "bad semantics");
     if (c->reserved != 0) return fail(LBM_EINVAL, "reserved must be 0");
+    if ((c->ext_f[0] == nullptr) != (c->ext_f[1] == nullptr))
+        return fail(LBM_EINVAL, "ext_f: give both population buffers or neither");
+    if (c->ext_f[0] && c->ext_f[0] == c->ext_f[1]) return fail(LBM_EINVAL, "ext_f: the two population buffers must differ");
     if (c->semantics == LBM_SEMANTICS_A) {
         if (c->collision != LBM_SRT || c->turb) return fail(LBM_EINVAL, "semantics A (MRT.py) is SRT without turbulence model");
         if (nyl != c->ny) return fail(LBM_EINVAL, "semantics A does not support y-strips");
@@ -1283,9 +1286,7 @@ int lbm_get_feq(lbm_handle_t s, void* feq, int on_device, void* stream) {
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     // equilibrium of the stored rho, u in the device layout of the macro planes, then the usual layout change
-    const long long n = (long long)s->cfg.batch * s->mplane;
     if (!s->scratch) CK(cudaMalloc(&s->scratch, s->state_bytes));            // >= 9 macro planes per cavity
-    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
     for (int b = 0; b < s->cfg.batch; ++b) {
         const size_t mo = (size_t)b * s->mplane * s->esz;
         char* out = (char*)s->scratch + 9 * mo;
@@ -1294,7 +1295,6 @@ int lbm_get_feq(lbm_handle_t s, void* feq, int on_device, void* stream) {
         else lbm_equ_kernel<float><<<nb, 256, 0, st>>>((const float*)((char*)s->rho + mo), (const float*)((char*)s->ux + mo), (const float*)((char*)s->uy + mo), (float*)out, s->mplane);
         s->launches++;
     }
-    (void)blocks;
     CK(cudaGetLastError());
     const size_t fcav = (size_t)9 * s->cfg.nx * s->nyl * s->esz;
     return move_planes(s, feq, fcav, on_device != 0, false, s->cfg.batch, 9, s->scratch, s->mplane, 9 * s->mplane, 0, st);

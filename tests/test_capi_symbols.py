@@ -98,3 +98,17 @@ def test_batch_limit_is_validated():
                        semantics=0, reserved=0)
     out = ctypes.c_size_t()
     assert lib.lbm_state_bytes(ctypes.byref(cfg), ctypes.byref(out)) == _capi.LBM_EINVAL
+
+
+def test_ext_buffers_come_in_pairs():
+    """Caller-owned population buffers (lbm_config_t.ext_f): both or neither, and two different ones -- checked before any
+    device is touched."""
+    from latticeboltzmannsimulations_b200 import _capi
+    lib = _capi.load()
+    out = ctypes.c_size_t()
+    for a, b in ((4096, 0), (0, 4096), (4096, 4096)):
+        cfg = _capi.Config(nx=8, ny=8, batch=1, dtype=1, collision=2, turb=0, y0=0, ny_local=0, device=-1, engine=0,
+                           semantics=0, reserved=0)
+        cfg.ext_f[0], cfg.ext_f[1] = a, b
+        assert lib.lbm_state_bytes(ctypes.byref(cfg), ctypes.byref(out)) == _capi.LBM_EINVAL
+        assert b"ext_f" in lib.lbm_last_error()
