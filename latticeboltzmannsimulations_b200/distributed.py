@@ -326,29 +326,64 @@ def shard_indices(n: int, rank: int, world: int) -> List[int]:
 
 
 def datagen_sharded(Re_list: Sequence[float], nx: int = 384, ny: int = 384, uLB: float = 0.08, steps: int = 10000,
-                    collision: str = "MRT", dtype="float32", group=None, gather: bool = True):
-    """Sharded sweep: each rank advances its own cavities; rank 0 assembles the reference's output arrays."""
+                    collision: str = "MRT", dtype="float32", group=None, gather: bool = True,
+                    out_dir: Optional[str] = None, return_steps: bool = False, **sweep):
+    """Sharded sweep: each rank advances its own cavities (``cavity.datagen`` on the cavities ``rank::world``, no
+    communication in the time loop); rank 0 assembles the reference's output arrays in the order of ``Re_list`` and,
+    with ``out_dir``, writes the four ``.npy`` files of ``MRT_GPU_datagen.py:899-902``.
+
+    ``sweep`` is forwarded to ``cavity.datagen``: ``turb``, ``converge``, ``Pinterval``, ``maxIt``, ``tol``, ``hits``
+    (the reference's defaults are SRT + ``turb=True`` run to its stopping rule), ``chunk``, ``device``, ``engine``.
+    Returns ``(f_final, u_final, feq_initial, Re_range[, steps_done])`` on rank 0 and ``None`` elsewhere; with
+    ``gather=False`` every rank gets ``(its cavity indices, its local datagen result)``.
+    """
     import torch.distributed as dist
-    from .cavity import datagen
+    from . import cavity
+    bad = set(sweep) - {"turb", "converge", "Pinterval", "maxIt", "tol", "hits", "chunk", "device", "engine"}
+    if bad:
+        raise TypeError("datagen_sharded() got unexpected keyword arguments %s" % sorted(bad))
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    Re_list = list(Re_list)
     mine = shard_indices(len(Re_list), rank, world)
-    local = datagen([Re_list[i] for i in mine], nx, ny, uLB, steps, collision, dtype) if mine else None
+    local = None
+    if mine:
+        local = cavity.datagen([Re_list[i] for i in mine], nx, ny, uLB, steps, collision, dtype, return_steps=True, **sweep)
     if not gather:
         return mine, local
     objs = [None] * world if rank == 0 else None
     dist.gather_object((mine, local), objs, dst=0, group=group)
     if rank != 0:
         return None
+    out = assemble_sweep(objs, Re_list, nx, ny, dtype)
+    if out_dir is not None:
+        cavity.save_dataset(out_dir, *out[:4])
+    return out if return_steps else out[:4]
+
+
+def assemble_sweep(parts, Re_list, nx: int, ny: int, dtype):
+    """Put the per-rank results ``[(cavity indices, datagen(..., return_steps=True) result or None), ...]`` back into
+    the order of ``Re_list``: ``(f_final[N,9,nx,ny], u_final[N,2,nx,ny], feq_initial[9,nx,ny], Re_range[N],
+    steps_done[N])``.  ``feq_initial`` is the same for every cavity (``rho = 1``, lid row at ``uLB``) and is taken from
+    the rank that owns cavity 0."""
+    from .cavity import _re_range_array
     n = len(Re_list)
     npdt = np.float32 if np.dtype(dtype) == np.float32 else np.float64
     f_final = np.empty((n, 9, nx, ny), npdt)
     u_final = np.empty((n, 2, nx, ny), npdt)
-    feq0 = None
-    for idx, loc in objs:
+    steps_done = np.zeros(n, np.int64)
+    feq0, seen = None, np.zeros(n, bool)
+    for idx, loc in parts:
         if not idx:
             continue
+        idx = list(idx)
+        if seen[idx].any():
+            raise ValueError("cavity assigned to more than one rank")
+        seen[idx] = True
         f_final[idx] = loc[0]
         u_final[idx] = loc[1]
-        feq0 = loc[2] if feq0 is None else feq0
-    from .cavity import _re_range_array
-    return f_final, u_final, feq0, _re_range_array(Re_list)
+        steps_done[idx] = loc[4]
+        if 0 in idx:
+            feq0 = loc[2]
+    if not seen.all():
+        raise ValueError("cavities %s were computed by no rank" % np.flatnonzero(~seen).tolist())
+    return f_final, u_final, feq0, _re_range_array(Re_list), steps_done

@@ -128,3 +128,68 @@ def test_strip_decomposition_gloo(world, nx, ny, deep):
     p = O.Params(nx, ny, Re=400, collision="MRT")
     want = O.run(p, steps, fin0=O.random_state(nx, ny, seed=3), form="pull")
     assert np.array_equal(f, want[2]) and np.array_equal(rho, want[0])
+
+
+def _fake_datagen(Re_list, nx, ny, uLB, steps, collision, dtype, return_steps=False, **kw):
+    """Stand-in for cavity.datagen on a box without a GPU: every array is filled with its cavity's Reynolds number."""
+    n = len(Re_list)
+    f = np.empty((n, 9, nx, ny), np.float32); u = np.empty((n, 2, nx, ny), np.float32)
+    for i, re in enumerate(Re_list):
+        f[i] = re; u[i] = -re
+    feq = np.full((9, nx, ny), 7.0, np.float32)
+    done = np.array([steps + int(re) for re in Re_list], np.int64)
+    assert kw == {"turb": True, "converge": True, "Pinterval": 50}
+    return f, u, feq, np.asarray(Re_list), done
+
+
+def _sweep_worker(rank, world, port, out_dir, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from latticeboltzmannsimulations_b200 import cavity, distributed
+        cavity.datagen = _fake_datagen
+        Re = list(range(100, 150, 10))                       # 5 cavities over 2 ranks: 3 + 2; over 7 ranks: some get none
+        res = distributed.datagen_sharded(Re, 6, 4, steps=1000, collision="SRT", out_dir=out_dir if rank == 0 else None,
+                                          return_steps=True, turb=True, converge=True, Pinterval=50)
+        mine, local = distributed.datagen_sharded(Re, 6, 4, steps=1000, gather=False, turb=True, converge=True, Pinterval=50)
+        assert mine == list(range(rank, 5, world)) and (local is None) == (not mine)
+        with pytest.raises(TypeError):
+            distributed.datagen_sharded(Re, 6, 4, stepz=3)
+        if rank == 0:
+            q.put(res)
+        else:
+            assert res is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 7])
+def test_sharded_sweep_assembly_gloo(world, tmp_path):
+    """datagen_sharded: cavity b -> rank b mod world, sweep options forwarded to every rank's datagen, results back in
+    the order of Re_list on rank 0 (also with ranks that own no cavity), dataset files written by rank 0."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    f, u, feq, Re, done = q.get(timeout=120)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    want = np.arange(100, 150, 10)
+    assert Re.dtype == np.int64 and np.array_equal(Re, want)
+    assert np.array_equal(f[:, 0, 0, 0], want) and np.array_equal(u[:, 1, 5, 3], -want) and np.all(feq == 7.0)
+    assert np.array_equal(done, 1000 + want)
+    assert np.array_equal(np.load(tmp_path / "f_final.npy"), f) and np.load(tmp_path / "Re_range.npy").dtype == np.int64
+    assert np.load(tmp_path / "u_final.npy").shape == (5, 2, 6, 4) and np.load(tmp_path / "feq_initial.npy").shape == (9, 6, 4)
+
+
+def test_assemble_sweep_rejects_gaps_and_overlaps():
+    from latticeboltzmannsimulations_b200.distributed import assemble_sweep
+    part = _fake_datagen([100, 120], 3, 3, 0.08, 10, "MRT", "float32", turb=True, converge=True, Pinterval=50)
+    with pytest.raises(ValueError, match="no rank"):
+        assemble_sweep([([0, 2], part)], [100, 110, 120], 3, 3, "float32")
+    with pytest.raises(ValueError, match="more than one"):
+        assemble_sweep([([0, 2], part), ([2, 1], part)], [100, 110, 120], 3, 3, "float32")
