@@ -116,7 +116,9 @@ int lbm_set_reynolds(lbm_handle_t h, int cavity, double uLB, double Re);
 int lbm_set_rates(lbm_handle_t h, int cavity, double uLB, double omega_nu, double omega_e,
                   double omega_eps, double omega_q, double omega_minus);
 
-/* Host init of MRT_GPU.py:259-267 + uploads :323-328: rho = 1, u = (uLB,0) on row y = 0, f = feq. */
+/* Host init of MRT_GPU.py:259-267 + uploads :323-328: rho = 1, u = (uLB,0) on row y = 0, f = feq.  Enqueued on the
+ * default (NULL) stream: a caller that steps on a non-blocking stream orders it after this call itself (event or
+ * lbm_sync). */
 int lbm_init_equilibrium(lbm_handle_t h);
 /* cuda.memcpy_htod(fin_g, fin) (MRT_GPU.py:323) incl. the [k,x,y]->[k,y,x] transposes of :283-289.
  * f: [batch][9][nx][ny_local] in the handle's dtype; on_device != 0 means `f` is a device pointer. */
