@@ -128,3 +128,15 @@ def test_live_compiled_allfunc():
     O.step_C(st, p)
     assert np.abs(st.rho - rho).max() <= 4.5e-16 and np.abs(st.u - u).max() <= 1e-16
     assert np.abs(st.fin - np.asarray(fin))[:, 1:-1, 1:-1].max() <= 2.3e-16
+
+
+def test_oracle_against_ghia_re100():
+    """The reference's only fixture for this path is GhiaData.csv (Re = 100 columns are the clean ones):
+    the oracle's C-MRT cavity at Re 100, run to its steady state on the CPU, reproduces the centre-line velocities of
+    Ghia et al. -- 96 x 96: 0.0093 / 0.0057 of uLB measured, the 128 x 128 figure of SURVEY.md 0-2 is 0.0091 / 0.0068."""
+    p = O.Params(96, 96, Re=100, collision="MRT")
+    rho, u, f = O.run_fast(p, 20000)
+    again = O.run_fast(p, 20500)[1]
+    assert np.abs(again - u).max() / 0.08 < 1e-4          # steady
+    ex, ey = O.ghia_errors(u, 0.08, O.load_ghia())
+    assert ex < 0.012 and ey < 0.009, (ex, ey)
