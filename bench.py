@@ -468,8 +468,9 @@ def run_multi_gpu(args, rank, world, local_rank):
                "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": wl, "description": desc, "collision": "MRT", "engine": sc.solver.engine,
-                          "decomposition": "%d y-strips of %d rows, 3 populations x %d values per interface and direction "
-                                           "per step over NCCL send/recv, %s" % (
+                          "decomposition": "%d y-strips of %d rows; per interface, direction and double step nine rows of %d "
+                                           "values (the 3 crossing populations of two rows + the 3 in-row ones of the edge "
+                                           "row, for the two-step kernel) in one NCCL send/recv, %s" % (
                                                world, sc.nyl, nx, "overlapped with the interior update" if sc.overlap else "not overlapped"),
                           "note": "the N=1 line runs cavity4096 (config 3) with the same kernels and reports the same-size "
                                   "single-GPU anchor as extra.cavity32768_f64_mlups",
@@ -521,6 +522,27 @@ def run_datagen(args, rank, world, local_rank):
             if world > 1:
                 t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
             res[dtype] = 256 * nx * ny * args.steps / ms / 1e3
+    # e2e: the public call of the sweep, datagen(Re_list, ...) -> f_final, u_final, feq_initial in host memory.  Its
+    # inputs are the Reynolds numbers (the equilibrium start is a function of them: MRT_GPU_datagen.py:259-267), its
+    # outputs the population and velocity fields of every cavity, downloaded inside the timed region.
+    try:
+        L.datagen(Re_all[mine][:2], nx, ny, steps=3, collision="MRT", dtype="float64")          # warm the call path
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = time.perf_counter()
+        f_fin, u_fin, feq0, _ = L.datagen(Re_all[mine], nx, ny, steps=args.steps, collision="MRT", dtype="float64")
+        e2e_s = time.perf_counter() - t
+        if world > 1:
+            tt = torch.tensor([e2e_s], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); e2e_s = float(tt.item())
+        assert np.isfinite(u_fin[:, :, ::17, ::17]).all()
+        e2e = {"value": round(256 * nx * ny * args.steps / e2e_s / 1e6, 1), "unit": "MLUPS",
+               "h2d_bytes_per_step": int(56 * 256 / args.steps),           # seven doubles of rates per cavity
+               "d2h_bytes_per_step": int((f_fin.nbytes + u_fin.nbytes + feq0.nbytes) * world / args.steps),
+               "call": "datagen(Re_list, 384, 384, steps=K) -> f_final, u_final, feq_initial in (pageable) host memory, per rank",
+               "seconds": round(e2e_s, 4)}
+    except Exception as exc:      # pragma: no cover
+        e2e = {"value": None, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(exc)}
     if rank == 0:
         gbs = res["float64"] * 144 / 1e3 / world * nl["float64"] / args.steps      # per launch (two steps when fused)
         out = {"metric": "MLUPS", "value": round(res["float64"], 1), "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
@@ -532,7 +554,7 @@ def run_datagen(args, rank, world, local_rank):
                "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
                             "traffic": None, "peak_source": peak_src, "per_gpu": True,
                             "algorithmic_bytes_per_node_per_launch": 144, "steps_per_launch": round(args.steps / nl["float64"], 3)},
-               "fp32": {"value": round(res["float32"], 1)}, "gpu_launches": int(nl["float64"])}
+               "fp32": {"value": round(res["float32"], 1)}, "e2e": e2e, "gpu_launches": int(nl["float64"])}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
