@@ -567,7 +567,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--engine", default="auto", choices=["auto", "ldg", "tma"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "ldg", "tma", "aa"])
     ap.add_argument("--no-overlap", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

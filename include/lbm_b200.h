@@ -41,8 +41,12 @@ enum lbm_region { LBM_REGION_ALL = 0, LBM_REGION_EDGE = 1, LBM_REGION_INTERIOR =
  * last rows/columns stale, "= feq" left wall) -- a compatibility mode so that BASELINE config 1 can be compared on
  * identical inputs; two simple passes per step, not tuned */
 enum lbm_semantics { LBM_SEMANTICS_C = 0, LBM_SEMANTICS_A = 1 };
-/* kernel family: plain coalesced loads, or TMA-staged persistent tiles */
-enum lbm_engine { LBM_ENGINE_AUTO = 0, LBM_ENGINE_LDG = 1, LBM_ENGINE_TMA = 2 };
+/* kernel family: plain coalesced loads (with the two-step kernels on top, the default), TMA-staged persistent tiles, or
+ * the AA pattern -- one-step kernels on ONE population buffer instead of the A/B pair (half the memory: a 32768^2 fp64
+ * cavity takes 77 GB instead of 155 GB; results bit-identical to the A/B one-step kernels; one lattice step per pass
+ * over memory, so about half the MLUPS of the two-step kernels).  AA handles hold whole cavities (no y-strips, no
+ * caller-owned buffers, no frozen cavities / convergence rule); lbm_download_f borrows a second buffer for the call. */
+enum lbm_engine { LBM_ENGINE_AUTO = 0, LBM_ENGINE_LDG = 1, LBM_ENGINE_TMA = 2, LBM_ENGINE_AA = 3 };
 
 typedef struct lbm_solver* lbm_handle_t;
 
@@ -202,7 +206,7 @@ int lbm_diagnostics(lbm_handle_t h, int cavity, void* ux_col, void* uy_row, int3
 int lbm_sync(lbm_handle_t h);
 /* Steps completed, and number of kernels this handle has launched (for the bench's gpu_launches). */
 int lbm_get_counters(lbm_handle_t h, int64_t* steps_done, int64_t* kernel_launches);
-/* Name of the kernel family in use ("ldg" / "tma"). */
+/* Name of the kernel family in use ("ldg" / "tma" / "aa"). */
 const char* lbm_engine_name(lbm_handle_t h);
 
 #ifdef __cplusplus

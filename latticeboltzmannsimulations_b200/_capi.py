@@ -15,10 +15,10 @@ LBM_OK, LBM_EINVAL, LBM_ECUDA, LBM_ENOMEM, LBM_ESTATE = 0, 1, 2, 3, 4
 LBM_F32, LBM_F64 = 0, 1
 LBM_SRT, LBM_TRT, LBM_MRT = 0, 1, 2
 LBM_REGION_ALL, LBM_REGION_EDGE, LBM_REGION_INTERIOR = 0, 1, 2
-LBM_ENGINE_AUTO, LBM_ENGINE_LDG, LBM_ENGINE_TMA = 0, 1, 2
+LBM_ENGINE_AUTO, LBM_ENGINE_LDG, LBM_ENGINE_TMA, LBM_ENGINE_AA = 0, 1, 2, 3
 
 COLLISIONS = {"SRT": LBM_SRT, "TRT": LBM_TRT, "MRT": LBM_MRT}
-ENGINES = {"auto": LBM_ENGINE_AUTO, "ldg": LBM_ENGINE_LDG, "tma": LBM_ENGINE_TMA}
+ENGINES = {"auto": LBM_ENGINE_AUTO, "ldg": LBM_ENGINE_LDG, "tma": LBM_ENGINE_TMA, "aa": LBM_ENGINE_AA}
 SEMANTICS = {"C": 0, "A": 1}
 
 # every symbol include/lbm_b200.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)

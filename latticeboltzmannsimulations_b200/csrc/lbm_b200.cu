@@ -23,6 +23,7 @@
 #include "lbm_device.cuh"
 #include "lbm_kernels.cuh"
 #include "lbm_fused2.cuh"
+#include "lbm_aa.cuh"
 #include "lbm_internal.h"
 #include "lbm_tma.cuh"
 
@@ -123,6 +124,9 @@ struct lbm_solver {
     int use_slide = 1;         // sliding-window two-step kernel for large cavities / batches (no closure)
     int slide_h = 0;           // rows per segment, 0 = chosen from the number of work items
     long long slide_min_nodes = LBM_SLIDE_MIN_NODES;
+    // AA pattern (LBM_ENGINE_AA, lbm_aa.cuh): one population buffer f[0]; f[1] stays NULL
+    bool aa = false;
+    bool aa_swapped = false;   // the buffer is in the SWAPPED layout (an odd number of AA steps since it was last NATURAL)
 };
 
 // A fresh state (init / upload) un-freezes every cavity; graphs captured with the old flag pointer are dropped.
@@ -393,6 +397,7 @@ static void launch_vec_coll(int coll, const StepArgs& a, const Launch& L, bool m
 // Which two-step (temporal blocking) kernel advances this handle, if any (whole cavity or y-strip of >= 2 rows).
 enum { TWO_NONE = 0, TWO_TILE = 1, TWO_SLIDE = 3 };
 static int two_step_kind(const lbm_solver* s) {
+    if (s->aa) return TWO_NONE;
     if (!s->use_fused2 || s->engine != LBM_ENGINE_LDG || s->cfg.semantics != LBM_SEMANTICS_C || s->nyl < 2) return TWO_NONE;
     const long long nodes = (long long)s->cfg.nx * s->cfg.ny * s->cfg.batch;
     if (nodes < s->fused2_min_nodes) return TWO_NONE;
@@ -598,6 +603,67 @@ static int launch_pass(lbm_solver* s, const void* src, void* dst, int row_begin,
     return LBM_OK;
 }
 
+// ---- AA pattern (one population buffer) ---------------------------------------------------------------------------
+template <typename T, int COLL, bool TURB>
+static void dispatch_aa_step(const StepArgs& a, const Launch& L, bool odd, bool walls, bool macros) {
+    if (odd) {
+        if (macros) launch_step(lbm_step_aa<T, COLL, true, true, true, MODE_STEP, TURB>, L, a);
+        else launch_step(lbm_step_aa<T, COLL, true, true, false, MODE_STEP, TURB>, L, a);
+    } else if (walls) {
+        if (macros) launch_step(lbm_step_aa<T, COLL, false, true, true, MODE_STEP, TURB>, L, a);
+        else launch_step(lbm_step_aa<T, COLL, false, true, false, MODE_STEP, TURB>, L, a);
+    } else {
+        if (macros) launch_step(lbm_step_aa<T, COLL, false, false, true, MODE_STEP, TURB>, L, a);
+        else launch_step(lbm_step_aa<T, COLL, false, false, false, MODE_STEP, TURB>, L, a);
+    }
+}
+
+template <typename T, int COLL>
+static void dispatch_aa_turb(const StepArgs& a, const Launch& L, bool odd, bool walls, bool macros) {
+    if (a.pi_eq) dispatch_aa_step<T, COLL, true>(a, L, odd, walls, macros);
+    else dispatch_aa_step<T, COLL, false>(a, L, odd, walls, macros);
+}
+
+template <typename T>
+static void dispatch_aa(int coll, const StepArgs& a, const Launch& L, bool odd, bool walls, bool macros, int mode) {
+    if (mode == MODE_FINALIZE) {
+        if (odd) launch_step(lbm_step_aa<T, COLL_MRT, true, true, false, MODE_FINALIZE>, L, a);
+        else launch_step(lbm_step_aa<T, COLL_MRT, false, true, false, MODE_FINALIZE>, L, a);
+        return;
+    }
+    if (mode == MODE_MACROS) {
+        if (odd) launch_step(lbm_step_aa<T, COLL_MRT, true, true, true, MODE_MACROS>, L, a);
+        else if (walls) launch_step(lbm_step_aa<T, COLL_MRT, false, true, true, MODE_MACROS>, L, a);
+        else launch_step(lbm_step_aa<T, COLL_MRT, false, false, true, MODE_MACROS>, L, a);
+        return;
+    }
+    switch (coll) {
+        case LBM_SRT: dispatch_aa_turb<T, COLL_SRT>(a, L, odd, walls, macros); break;
+        case LBM_TRT: dispatch_aa_turb<T, COLL_TRT>(a, L, odd, walls, macros); break;
+        default: dispatch_aa_turb<T, COLL_MRT>(a, L, odd, walls, macros); break;
+    }
+}
+
+// One AA pass over the whole cavity.  MODE_STEP works in place on f[0]; MODE_FINALIZE writes the reference's `fin` into
+// `out` (a second buffer borrowed for a download); MODE_MACROS only stores rho, u.  odd = the buffer is in the SWAPPED
+// layout; walls = rebuild what a wall node cannot receive (false only for a freshly uploaded / initialised state).
+static int launch_aa_pass(lbm_solver* s, bool odd, bool walls, bool macros, int mode, void* out, cudaStream_t st) {
+    StepArgs a = make_args(s, s->f[0], mode == MODE_STEP ? s->f[0] : out);
+    Launch L{};
+    L.st = st;
+    L.pdl = s->use_pdl && mode == MODE_STEP;
+    for (int off = 0; off < s->nyl; off += 65535) {
+        const int n = s->nyl - off < 65535 ? s->nyl - off : 65535;
+        a.row_begin = off; a.row_stride = 1; a.row_count = n;
+        block_shape(s->cfg.nx, n, s->cfg.batch, &L);
+        if (s->cfg.dtype == LBM_F64) dispatch_aa<double>(s->cfg.collision, a, L, odd, walls, macros, mode);
+        else dispatch_aa<float>(s->cfg.collision, a, L, odd, walls, macros, mode);
+        s->launches++;
+    }
+    CK(cudaGetLastError());
+    return LBM_OK;
+}
+
 // Row bands of a one-step region launch.  EDGE = the first TWO and the last TWO rows of the strip: the halo exchange
 // that follows an EDGE launch (while INTERIOR is still running) ships rows 0, 1, nyl-2 and nyl-1 -- the second ones
 // feed the neighbour's second ghost rows for the two-step kernel -- so all four must be complete by then.
@@ -644,7 +710,7 @@ static int check_cfg(const lbm_config_t* c, int* nyl_out) {
     int nyl = c->ny_local == 0 ? c->ny : c->ny_local;
     if (c->ny_local == 0 && c->y0 != 0) return fail(LBM_EINVAL, "y0 must be 0 when ny_local == 0");
     if (c->y0 < 0 || nyl < 1 || c->y0 + nyl > c->ny) return fail(LBM_EINVAL, "y-strip [y0, y0+ny_local) outside [0, ny)");
-    if (c->engine < LBM_ENGINE_AUTO || c->engine > LBM_ENGINE_TMA) return fail(LBM_EINVAL, "bad engine");
+    if (c->engine < LBM_ENGINE_AUTO || c->engine > LBM_ENGINE_AA) return fail(LBM_EINVAL, "bad engine");
     if (c->semantics != LBM_SEMANTICS_C && c->semantics != LBM_SEMANTICS_A) return fail(LBM_EINVAL, "bad semantics");
     if (c->reserved != 0) return fail(LBM_EINVAL, "reserved must be 0");
     if ((c->ext_f[0] == nullptr) != (c->ext_f[1] == nullptr))
@@ -654,6 +720,11 @@ static int check_cfg(const lbm_config_t* c, int* nyl_out) {
         if (c->collision != LBM_SRT || c->turb) return fail(LBM_EINVAL, "semantics A (MRT.py) is SRT without turbulence model");
         if (nyl != c->ny) return fail(LBM_EINVAL, "semantics A does not support y-strips");
         if (c->ny > 65535) return fail(LBM_EINVAL, "semantics A supports ny <= 65535");
+    }
+    if (c->engine == LBM_ENGINE_AA) {
+        if (c->semantics != LBM_SEMANTICS_C) return fail(LBM_EINVAL, "the AA pattern implements semantics C");
+        if (nyl != c->ny) return fail(LBM_EINVAL, "the AA pattern holds whole cavities (no y-strips)");
+        if (c->ext_f[0]) return fail(LBM_EINVAL, "the AA pattern owns its single population buffer (no ext_f)");
     }
     *nyl_out = nyl;
     return LBM_OK;
@@ -725,6 +796,7 @@ int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
     s->plane = L.plane; s->cavity = L.cavity; s->mplane = (long long)nyl * L.pitch;
     s->state_bytes = (size_t)L.state_bytes;
     s->engine = cfg->engine == LBM_ENGINE_TMA ? LBM_ENGINE_TMA : LBM_ENGINE_LDG;   // AUTO -> ldg
+    s->aa = cfg->engine == LBM_ENGINE_AA;
 #define CKD(call)                                                                       \
     do {                                                                                \
         cudaError_t e__ = (call);                                                       \
@@ -740,12 +812,12 @@ int lbm_create(const lbm_config_t* cfg, lbm_handle_t* out) {
     } else {
         s->own_f = true;
         CKD(cudaMalloc(&s->f[0], s->state_bytes));
-        CKD(cudaMalloc(&s->f[1], s->state_bytes));
+        if (!s->aa) CKD(cudaMalloc(&s->f[1], s->state_bytes));
     }
     // ghost rows and pitch padding must hold finite values: they are read (and discarded) by masked lanes only in
     // the TMA family, but zero them once for determinism.
     CKD(cudaMemset(s->f[0], 0, s->state_bytes));
-    CKD(cudaMemset(s->f[1], 0, s->state_bytes));
+    if (s->f[1]) CKD(cudaMemset(s->f[1], 0, s->state_bytes));
     const size_t mbytes = (size_t)cfg->batch * s->mplane * s->esz;
     CKD(cudaMalloc(&s->rho, mbytes));
     CKD(cudaMalloc(&s->ux, mbytes));
@@ -870,7 +942,7 @@ int lbm_init_equilibrium(lbm_handle_t s) {
         s->launches++;
     }
     CK(cudaGetLastError());
-    s->cur = 0; s->pre = true; s->steps = 0;
+    s->cur = 0; s->pre = true; s->steps = 0; s->aa_swapped = false;
     reset_active(s);
     return LBM_OK;
 }
@@ -992,7 +1064,7 @@ int lbm_upload_f(lbm_handle_t s, const void* f, int on_device, void* stream) {
         s->launches++;
     }
     CK(cudaGetLastError());
-    s->cur = 0; s->pre = true; s->steps = 0;
+    s->cur = 0; s->pre = true; s->steps = 0; s->aa_swapped = false;
     reset_active(s);
     return LBM_OK;
 }
@@ -1004,6 +1076,18 @@ int lbm_download_f(lbm_handle_t s, void* f, int on_device, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     rc = sync_params(s, st);
     if (rc) return rc;
+    if (s->aa) {
+        const size_t fc = (size_t)9 * s->cfg.nx * s->nyl * s->esz;
+        if (s->pre) return move_planes(s, f, fc, on_device != 0, false, s->cfg.batch, 9, s->f[0], s->plane, s->cavity, s->pitch, st);
+        // the reference's `fin` (gather + wall rule, no collision) needs a second buffer: borrowed for this call only
+        if (!s->scratch) CK(cudaMalloc(&s->scratch, s->state_bytes));
+        rc = launch_aa_pass(s, s->aa_swapped, true, false, MODE_FINALIZE, s->scratch, st);
+        if (rc == LBM_OK)
+            rc = move_planes(s, f, fc, on_device != 0, false, s->cfg.batch, 9, s->scratch, s->plane, s->cavity, s->pitch, st);
+        cudaFree(s->scratch);              // synchronises the device: everything queued above has run
+        s->scratch = nullptr;
+        return rc;
+    }
     void* fin = s->f[s->cur];
     if (!s->pre) {
         // gather + wall rule (no collision) into the buffer the next step will overwrite anyway -- except with frozen
@@ -1037,6 +1121,7 @@ static int step_A(lbm_solver* s, cudaStream_t st) {
 int lbm_step_region(lbm_handle_t s, int region, int write_macros, void* stream) {
     if (!s) return fail(LBM_EINVAL, "NULL handle");
     if (s->cfg.semantics == LBM_SEMANTICS_A) return fail(LBM_ESTATE, "semantics A has no region stepping: use lbm_step");
+    if (s->aa) return fail(LBM_ESTATE, "the AA pattern has no region stepping: use lbm_step");
     int rc = set_device(s);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1055,7 +1140,7 @@ int lbm_step_region(lbm_handle_t s, int region, int write_macros, void* stream) 
 
 int lbm_swap(lbm_handle_t s) {
     if (!s) return fail(LBM_EINVAL, "NULL handle");
-    if (s->cfg.semantics == LBM_SEMANTICS_A) return fail(LBM_ESTATE, "semantics A has no region stepping: use lbm_step");
+    if (s->cfg.semantics == LBM_SEMANTICS_A || s->aa) return fail(LBM_ESTATE, "semantics A and the AA pattern have no region stepping: use lbm_step");
     s->cur ^= 1; s->pre = false; s->steps++;
     return LBM_OK;
 }
@@ -1102,7 +1187,7 @@ int lbm_step2_region(lbm_handle_t s, int region, int write_macros, void* stream)
 
 int lbm_swap2(lbm_handle_t s) {
     if (!s) return fail(LBM_EINVAL, "NULL handle");
-    if (s->cfg.semantics == LBM_SEMANTICS_A) return fail(LBM_ESTATE, "semantics A has no region stepping: use lbm_step");
+    if (s->cfg.semantics == LBM_SEMANTICS_A || s->aa) return fail(LBM_ESTATE, "semantics A and the AA pattern have no region stepping: use lbm_step");
     s->cur ^= 1; s->side ^= 1; s->steps += 2;
     return LBM_OK;
 }
@@ -1128,7 +1213,7 @@ static HaloRows halo_rows(const lbm_solver* s, int dir, bool pack) {
 static int halo_move(lbm_solver* s, int dir, void* buf, bool pack, cudaStream_t st) {
     if (!buf) return fail(LBM_EINVAL, "NULL buffer");
     if (dir != 0 && dir != 1) return fail(LBM_EINVAL, "dir must be 0 (strip above) or 1 (strip below)");
-    if (s->cfg.batch != 1 || s->nyl < 2) return fail(LBM_ESTATE, "packed halo rows need a single-cavity strip of >= 2 rows");
+    if (s->cfg.batch != 1 || s->nyl < 2 || s->aa) return fail(LBM_ESTATE, "packed halo rows need a single-cavity A/B strip of >= 2 rows");
     int rc = set_device(s);
     if (rc) return rc;
     char* f = (char*)s->f[s->cur ^ 1];                                  // the buffer written by the step in progress
@@ -1159,7 +1244,7 @@ int lbm_halo_unpack(lbm_handle_t s, int dir, const void* buf, void* stream) {
 
 int lbm_buffer_ptr(lbm_handle_t s, int which, void** ptr) {
     if (!s || !ptr) return fail(LBM_EINVAL, "NULL argument");
-    *ptr = s->f[which ? (s->cur ^ 1) : s->cur];
+    *ptr = s->aa ? s->f[0] : s->f[which ? (s->cur ^ 1) : s->cur];
     return LBM_OK;
 }
 
@@ -1212,6 +1297,14 @@ int lbm_step(lbm_handle_t s, int nsteps, int write_macros, void* stream) {
     if (rc) return rc;
     if (s->cfg.semantics == LBM_SEMANTICS_A) {
         for (int i = 0; i < nsteps; ++i) { rc = step_A(s, st); if (rc) return rc; }
+        return LBM_OK;
+    }
+    if (s->aa) {
+        for (int i = 0; i < nsteps; ++i) {
+            rc = launch_aa_pass(s, s->aa_swapped, !s->pre, write_macros && i == nsteps - 1, MODE_STEP, nullptr, st);
+            if (rc) return rc;
+            s->aa_swapped = !s->aa_swapped; s->pre = false; s->steps++;
+        }
         return LBM_OK;
     }
     int left = nsteps;
@@ -1275,7 +1368,8 @@ int lbm_get_macros_current(lbm_handle_t s, void* rho, void* u, int on_device, vo
     cudaStream_t st = (cudaStream_t)stream;
     rc = sync_params(s, st);
     if (rc) return rc;
-    rc = launch_pass(s, s->f[s->cur], s->f[s->cur ^ 1], 0, s->nyl, 1, !s->pre, true, MODE_MACROS, st);
+    if (s->aa) rc = launch_aa_pass(s, s->aa_swapped, !s->pre, true, MODE_MACROS, nullptr, st);
+    else rc = launch_pass(s, s->f[s->cur], s->f[s->cur ^ 1], 0, s->nyl, 1, !s->pre, true, MODE_MACROS, st);
     if (rc) return rc;
     return macros_out(s, rho, u, on_device, st);
 }
@@ -1297,7 +1391,9 @@ int lbm_get_feq(lbm_handle_t s, void* feq, int on_device, void* stream) {
     }
     CK(cudaGetLastError());
     const size_t fcav = (size_t)9 * s->cfg.nx * s->nyl * s->esz;
-    return move_planes(s, feq, fcav, on_device != 0, false, s->cfg.batch, 9, s->scratch, s->mplane, 9 * s->mplane, 0, st);
+    const int rc2 = move_planes(s, feq, fcav, on_device != 0, false, s->cfg.batch, 9, s->scratch, s->mplane, 9 * s->mplane, 0, st);
+    if (s->aa) { cudaFree(s->scratch); s->scratch = nullptr; }     // an AA handle keeps no second buffer around
+    return rc2;
 }
 
 int lbm_equilibrium(int dtype, int64_t n, const void* rho, const void* ux, const void* uy, void* feq, int on_device,
@@ -1423,6 +1519,7 @@ int lbm_mean_u(lbm_handle_t s, double* mean_out, void* stream) {
 
 int lbm_set_active(lbm_handle_t s, const int32_t* active, void* stream) {
     if (!s || !active) return fail(LBM_EINVAL, "NULL argument");
+    if (s->aa) return fail(LBM_ESTATE, "the AA pattern cannot freeze cavities (one buffer, one phase for the whole batch)");
     if (s->pre) return fail(LBM_ESTATE, "cavities can be frozen only after at least one step (post-collision state)");
     int rc = set_device(s);
     if (rc) return rc;
@@ -1472,6 +1569,7 @@ int lbm_set_active(lbm_handle_t s, const int32_t* active, void* stream) {
 int lbm_converge_check(lbm_handle_t s, double tol, int hits, int32_t* active_out, void* stream) {
     if (!s) return fail(LBM_EINVAL, "NULL handle");
     if (!(tol > 0.0) || hits < 1) return fail(LBM_EINVAL, "tol must be positive and hits >= 1");
+    if (s->aa) return fail(LBM_ESTATE, "the AA pattern cannot retire cavities: use an A/B handle for the convergence rule");
     if (s->pre) return fail(LBM_ESTATE, "the convergence check needs at least one step (stored velocity field)");
     if (s->nyl != s->cfg.ny) return fail(LBM_ESTATE, "the convergence check needs whole cavities");
     int rc = set_device(s);
@@ -1542,7 +1640,7 @@ int lbm_get_counters(lbm_handle_t s, int64_t* steps_done, int64_t* kernel_launch
 
 const char* lbm_engine_name(lbm_handle_t s) {
     if (!s) return "";
-    return s->engine == LBM_ENGINE_TMA ? "tma" : "ldg";
+    return s->aa ? "aa" : (s->engine == LBM_ENGINE_TMA ? "tma" : "ldg");
 }
 
 }  // extern "C"

@@ -112,3 +112,21 @@ def test_ext_buffers_come_in_pairs():
         cfg.ext_f[0], cfg.ext_f[1] = a, b
         assert lib.lbm_state_bytes(ctypes.byref(cfg), ctypes.byref(out)) == _capi.LBM_EINVAL
         assert b"ext_f" in lib.lbm_last_error()
+
+
+def test_aa_engine_configuration_is_validated():
+    """LBM_ENGINE_AA (one population buffer): whole cavities of semantics C that own their buffer."""
+    from latticeboltzmannsimulations_b200 import _capi
+    lib = _capi.load()
+    out = ctypes.c_size_t()
+    base = dict(nx=64, ny=64, batch=2, dtype=1, collision=2, turb=1, y0=0, ny_local=0, device=-1,
+                engine=_capi.ENGINES["aa"], semantics=0, reserved=0)
+    assert lib.lbm_state_bytes(ctypes.byref(_capi.Config(**base)), ctypes.byref(out)) == 0 and out.value > 0
+    for change, word in ((dict(ny_local=32), b"whole"), (dict(semantics=1, collision=0, turb=0), b"semantics"),
+                         (dict(engine=4), b"engine")):
+        cfg = _capi.Config(**dict(base, **change))
+        assert lib.lbm_state_bytes(ctypes.byref(cfg), ctypes.byref(out)) == _capi.LBM_EINVAL
+        assert word in lib.lbm_last_error(), lib.lbm_last_error()
+    cfg = _capi.Config(**base)
+    cfg.ext_f[0], cfg.ext_f[1] = 4096, 8192
+    assert lib.lbm_state_bytes(ctypes.byref(cfg), ctypes.byref(out)) == _capi.LBM_EINVAL and b"ext_f" in lib.lbm_last_error()
