@@ -2,7 +2,8 @@
 // Built by tests/host_emu/build_emu.py with g++ (-ffp-contract=off: like the library's -fmad=false, every fused
 // multiply-add is the explicit fm() of lbm_device.cuh).  Mirrors, for one whole cavity, what lbm_b200.cu does around the
 // kernels: device layout [k][row + 1][pitch], side buffers, init / upload seeding, A/B ping-pong or the AA phases,
-// finalize pass for the download.  family 0 = lbm_step_ldg (A/B), 1 = lbm_step_aa (single buffer).
+// finalize pass for the download.  family 0 = lbm_step_ldg (A/B), 1 = lbm_step_aa (single buffer), 2 = the semantics-A passes
+// (lbm_A_collide + lbm_A_stream_bc, SRT only).
 #include <cuda_runtime.h>      // the stub
 
 #include <vector>
@@ -86,6 +87,17 @@ static int run(int family, int nx, int ny, int steps, const CavityParams& cp, co
     }
     int cur = 0;
     bool pre = true, swapped = false;
+    if (family == 2) {
+        // semantics A (the two plain passes of step_A in lbm_b200.cu): collide f[0] -> f[1], stream + walls f[1] -> f[0] in place
+        buf[1].assign(cavity, (T)0);
+        for (int i = 0; i < steps; ++i) {
+            a.src = buf[0].data(); a.dst = buf[1].data();
+            launch(lbm_A_collide<T>, a, nx, ny, 1);
+            a.src = buf[1].data(); a.dst = buf[0].data();
+            launch(lbm_A_stream_bc<T>, a, nx, ny, 1);
+        }
+        steps = 0;       // nothing left for the loops below; f[0] is `fin`, rho / u are the step's own moments
+    }
     for (int i = 0; i < steps; ++i) {
         const bool macros = (i == steps - 1);
         if (family == 0) {

@@ -106,3 +106,19 @@ def test_aa_pattern_minimum_sizes_and_against_the_oracle(emu):
     p = O.Params(48, 48, Re=1000.0, collision="SRT", turb=1)
     close(run_emu(emu, 1, "float64", p, 200), O.run_fast(p, 200), "float64")
     close(run_emu(emu, 1, "float32", p, 201), O.run_fast(p, 201), "float32")
+
+
+@pytest.mark.parametrize("name", ["ref_A_32x32_Re100_N25.npz", "ref_A_40x24_Re400_N60.npz"])
+def test_semantics_A_kernel_source_against_the_real_MRT_py(emu, name):
+    """The compatibility mode's two passes (lbm_A_collide, lbm_A_stream_bc) against OUTPUTS OF THE REAL MRT.py (goldens
+    written by executing the reference script, tests/golden/make_golden.py): BASELINE config 1 semantics, on the CPU."""
+    d = np.load(os.path.join(HERE, "golden", name))
+    nx, ny, Re, n, uLB = d["meta"]
+    p = O.Params(int(nx), int(ny), uLB=float(uLB), Re=float(Re), collision="SRT")
+    close(run_emu(emu, 2, "float64", p, int(n)), (d["rho"], d["u"], d["fin"]), "float64", float(uLB))
+    close(run_emu(emu, 2, "float32", p, int(n)), (d["rho"], d["u"], d["fin"]), "float32", float(uLB))
+    # from a random state too, against the oracle's restatement of MRT.py, incl. the rows / columns its slices never reach
+    f0 = O.random_state(int(nx), int(ny), seed=8)
+    got = run_emu(emu, 2, "float64", p, 40, f0)
+    close(got, O.run(p, 40, semantics="A", fin0=f0), "float64", float(uLB))
+    assert np.array_equal(got[2][3, int(nx) - 2, 1:-1], f0[3, int(nx) - 2, 1:-1])
