@@ -371,7 +371,8 @@ def run_single_gpu(args):
                         "frac": round(r64["gbs"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
                         "traffic_source": traffic_src or "not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum "
                                                          "per launch from the ncu capture summarised under profiles/",
-                        "kernel": "lbm_step_slide2 (two lattice steps per launch)" if r64["steps_per_launch"] > 1.5 else "lbm_step_ldg",
+                        "kernel": ("lbm_step_aa (AA pattern, one buffer)" if r64["engine"] == "aa" else
+                                   "lbm_step_slide2 (two lattice steps per launch)" if r64["steps_per_launch"] > 1.5 else "lbm_step_ldg"),
                         "algorithmic_bytes_per_node_per_launch": 144, "nodes_per_launch": nx * ny,
                         "steps_per_launch": round(r64["steps_per_launch"], 3),
                         "frac_of_nominal_8TBs": round(r64["gbs"] / 8000.0, 4),
