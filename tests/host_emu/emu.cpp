@@ -185,3 +185,34 @@ extern "C" int emu_run(int family, int is_f64, int coll, int turb, int nx, int n
     if (is_f64) return run_c<double>(family, coll, turb, nx, ny, steps, cp, f0, f_out, rho_out, u_out, rho_cur, u_cur);
     return run_c<float>(family, coll, turb, nx, ny, steps, cp, f0, f_out, rho_out, u_out, rho_cur, u_cur);
 }
+
+// ---- y-strips: the one-step kernel on caller-owned device-layout buffers -------------------------------------------
+// One launch of lbm_step_ldg (fp64, MRT) over the local rows [row_begin, row_begin + row_count) of a strip that owns
+// global rows [y0, y0 + nyl): src / dst are [9][nyl + 2][pitch] with one ghost row above and below (lbm_layout_t), the
+// side buffers as in the library.  mode: 0 step (gather != 0 after the first step), 1 finalize (download), 3 initial
+// equilibrium into dst (lbm_init_eq).  What tests/test_distributed_cpu.py runs under gloo between two halo exchanges.
+extern "C" int emu_strip_pass(int mode, int gather, int macros, int nx, int ny, int y0, int nyl, const double* rates,
+                              const double* src, double* dst, double* rho, double* ux, double* uy, double* rho_lid,
+                              double* carry, int row_begin, int row_count) {
+    CavityParams cav{};
+    cav.uLB = rates[0]; cav.omega = rates[1]; cav.omegam = rates[2]; cav.s_e = rates[3]; cav.s_eps = rates[4]; cav.s_q = rates[5];
+    cav.tau0 = rates[6];
+    StepArgs a{};
+    const int pitch = (nx + 31) / 32 * 32;
+    a.src = src; a.dst = dst; a.rho = rho; a.ux = ux; a.uy = uy;
+    a.rho_lid = rho_lid; a.carry = carry; a.rho_lid_out = rho_lid; a.carry_out = carry;
+    a.cav = &cav;
+    a.nx = nx; a.ny = ny; a.y0 = y0; a.nyl = nyl; a.pitch = pitch;
+    a.plane = (long long)(nyl + 2) * pitch; a.cavity = 9 * a.plane; a.mplane = (long long)nyl * pitch;
+    a.row_begin = row_begin; a.row_stride = 1; a.row_count = row_count;
+    if (mode == 3) { launch(lbm_init_eq<double>, a, nx, nyl, 1); return 0; }
+    if (mode == 1) { launch(lbm_step_ldg<double, COLL_MRT, true, false, MODE_FINALIZE>, a, nx, row_count, 1); return 0; }
+    if (gather) {
+        if (macros) launch(lbm_step_ldg<double, COLL_MRT, true, true, MODE_STEP>, a, nx, row_count, 1);
+        else launch(lbm_step_ldg<double, COLL_MRT, true, false, MODE_STEP>, a, nx, row_count, 1);
+    } else {
+        if (macros) launch(lbm_step_ldg<double, COLL_MRT, false, true, MODE_STEP>, a, nx, row_count, 1);
+        else launch(lbm_step_ldg<double, COLL_MRT, false, false, MODE_STEP>, a, nx, row_count, 1);
+    }
+    return 0;
+}

@@ -193,3 +193,94 @@ def test_assemble_sweep_rejects_gaps_and_overlaps():
         assemble_sweep([([0, 2], part)], [100, 110, 120], 3, 3, "float32")
     with pytest.raises(ValueError, match="more than one"):
         assemble_sweep([([0, 2], part), ([2, 1], part)], [100, 110, 120], 3, 3, "float32")
+
+
+def _load_emu():
+    """tests/host_emu: the product's one-step kernel source compiled for the host (see tests/test_host_emulation.py)."""
+    import ctypes as C
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(here, "host_emu", "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = C.CDLL(mod.build())
+    dp = C.POINTER(C.c_double)
+    lib.emu_strip_pass.argtypes = [C.c_int] * 7 + [dp] * 8 + [C.c_int] * 2
+    lib.emu_run.argtypes = [C.c_int] * 7 + [dp] * 7
+    return lib, dp
+
+
+def _kernel_strip_worker(rank, world, port, nx, ny, steps, q):
+    """One rank of a y-strip run made of the PRODUCT's parts on the CPU: the one-step kernel source (emulated node by
+    node) on the strip's device-layout buffers, the product's HaloExchanger over gloo between the steps, in the product's
+    order -- edge rows, exchange, interior rows."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lib, dp = _load_emu()
+        p = O.Params(nx, ny, Re=400, collision="MRT")
+        rates = np.array([p.uLB, p.omega, p.omegam, p.omega_e, p.omega_eps, p.omega_q, 1.0 / p.omega])
+        y0, nyl = partition_rows(ny, world)[rank]
+        pitch = (nx + 31) // 32 * 32
+        bufs = [torch.zeros(9, nyl + 2, pitch, dtype=torch.float64) for _ in range(2)]
+        rho, ux, uy = (np.zeros((nyl, pitch)) for _ in range(3))
+        rho_lid, carry = np.zeros(pitch), np.zeros(4)
+        import ctypes
+        ptr = lambda a: a.ctypes.data_as(dp)
+        tptr = lambda t: ctypes.cast(t.data_ptr(), dp)
+
+        def launch(mode, gather, macros, src, dst, r0, n):
+            assert lib.emu_strip_pass(mode, gather, macros, nx, ny, y0, nyl, ptr(rates), tptr(src), tptr(dst), ptr(rho), ptr(ux),
+                                      ptr(uy), ptr(rho_lid), ptr(carry), r0, n) == 0
+
+        ex = HaloExchanger(bufs, nx, rank, world)
+        launch(3, 0, 0, bufs[0], bufs[0], 0, nyl)                       # lbm_init_equilibrium
+        which = 0
+        for i in range(steps):
+            src, dst, last = bufs[which], bufs[which ^ 1], int(i == steps - 1)
+            if nyl >= 5:                                               # LBM_REGION_EDGE, exchange, LBM_REGION_INTERIOR
+                launch(0, int(i > 0), last, src, dst, 0, 2)
+                launch(0, int(i > 0), last, src, dst, nyl - 2, 2)
+                works = ex.exchange(which ^ 1)
+                launch(0, int(i > 0), last, src, dst, 2, nyl - 4)
+            else:
+                launch(0, int(i > 0), last, src, dst, 0, nyl)
+                works = ex.exchange(which ^ 1)
+            for w in works:
+                w.wait()
+            which ^= 1
+        launch(1, 1, 0, bufs[which], bufs[which ^ 1], 0, nyl)           # the download's finalize pass
+        fin = bufs[which ^ 1][:, 1:nyl + 1, :nx].numpy().transpose(0, 2, 1).copy()
+        out = [None] * world if rank == 0 else None
+        dist.gather_object((fin, rho[:, :nx].T.copy()), out, dst=0)
+        if rank == 0:
+            q.put((np.concatenate([o[0] for o in out], axis=2), np.concatenate([o[1] for o in out], axis=1)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nx,ny", [(2, 40, 26), (3, 33, 13)])
+def test_product_kernel_and_exchanger_in_strips_gloo(world, nx, ny):
+    """Strips of the product's own kernel source + the product's halo exchanger equal the single-domain run of the same
+    kernel BIT FOR BIT (and the oracle to 1e-12): the N > 1 data path, minus the GPU, on world_size 2 and 3."""
+    steps = 15
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_kernel_strip_worker, args=(r, world, port, nx, ny, steps, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    f, rho = q.get(timeout=180)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    lib, dp = _load_emu()
+    p = O.Params(nx, ny, Re=400, collision="MRT")
+    rates = np.array([p.uLB, p.omega, p.omegam, p.omega_e, p.omega_eps, p.omega_q, 1.0 / p.omega])
+    f1 = np.empty((9, nx, ny)); rho1 = np.empty((nx, ny)); u1 = np.empty((2, nx, ny))
+    ptr = lambda a: a.ctypes.data_as(dp)
+    assert lib.emu_run(0, 1, 2, 0, nx, ny, steps, ptr(rates), None, ptr(f1), ptr(rho1), ptr(u1), None, None) == 0
+    assert np.array_equal(f, f1) and np.array_equal(rho, rho1)
+    want = O.run(p, steps, form="pull")
+    assert np.abs(f - want[2]).max() < 1e-12 and np.abs(rho - want[0]).max() < 1e-12
