@@ -67,6 +67,7 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), fn
                 assert "lbm_oracle" not in txt.replace("oracle/lbm_oracle.py", ""), fn
+                assert "host_emu" not in txt, fn          # the CPU emulation of the kernel source is test-only too
 
 
 def test_functions_shim_signature_errors():
