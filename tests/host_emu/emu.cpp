@@ -216,3 +216,16 @@ extern "C" int emu_strip_pass(int mode, int gather, int macros, int nx, int ny, 
     }
     return 0;
 }
+
+// functions.equ through lbm_equ_kernel (fp64): feq[9][n] from rho[n], ux[n], uy[n], a grid-stride launch of 3 x 2 threads
+extern "C" int emu_equ(long long n, const double* rho, const double* ux, const double* uy, double* feq) {
+    blockDim = dim3(2, 1, 1);
+    gridDim = dim3(3, 1, 1);
+    for (unsigned b = 0; b < 3; ++b)
+        for (unsigned t = 0; t < 2; ++t) {
+            blockIdx.x = b; blockIdx.y = 0; blockIdx.z = 0;
+            threadIdx.x = t; threadIdx.y = 0; threadIdx.z = 0;
+            lbm_equ_kernel<double>(rho, ux, uy, feq, n);
+        }
+    return 0;
+}

@@ -122,3 +122,18 @@ def test_semantics_A_kernel_source_against_the_real_MRT_py(emu, name):
     got = run_emu(emu, 2, "float64", p, 40, f0)
     close(got, O.run(p, 40, semantics="A", fin0=f0), "float64", float(uLB))
     assert np.array_equal(got[2][3, int(nx) - 2, 1:-1], f0[3, int(nx) - 2, 1:-1])
+
+
+def test_equ_kernel_source_is_the_reference_expression_bitwise(emu):
+    """`functions.equ` (functions.pyx:229-267 == MRT.py:213-231) through lbm_equ_kernel: the reference's operation order
+    without any fused operation, hence the same bits as the NumPy expression of the oracle -- and as the compiled
+    reference module's output stored with the golden vectors."""
+    rng = np.random.default_rng(3)
+    n = 1000
+    rho = 1 + 0.05 * rng.uniform(-1, 1, n); ux = 0.1 * rng.uniform(-1, 1, n); uy = 0.1 * rng.uniform(-1, 1, n)
+    feq = np.empty((9, n))
+    dp = C.POINTER(C.c_double)
+    emu.emu_equ.argtypes = [C.c_longlong] + [dp] * 4
+    assert emu.emu_equ(n, *[a.ctypes.data_as(dp) for a in (rho, ux, uy, feq)]) == 0
+    want = O.equ(rho.reshape(n, 1), np.stack([ux, uy]).reshape(2, n, 1))[:, :, 0]
+    assert np.array_equal(feq, want)
