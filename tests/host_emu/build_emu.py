@@ -18,14 +18,21 @@ def build(force: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) > max(os.path.getmtime(s) for s in srcs):
         return LIB
     os.makedirs(OUT, exist_ok=True)
-    with open(os.path.join(CSRC, "lbm_kernels.cuh")) as fh:
-        text = "".join(line for line in fh if "griddepcontrol" not in line)
-    with open(os.path.join(OUT, "lbm_kernels_nopdl.cuh"), "w") as fh:
-        fh.write(text)
-    tmp = LIB + ".%d.tmp" % os.getpid()
-    subprocess.check_call([GXX, "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
-                           "-I", os.path.join(HERE, "stub"), "-I", OUT, "-I", CSRC, os.path.join(HERE, "emu.cpp"), "-o", tmp])
-    os.replace(tmp, LIB)
+    import fcntl
+    with open(os.path.join(OUT, ".lock"), "w") as lock:        # several test processes may get here together
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and os.path.exists(LIB) and os.path.getmtime(LIB) > max(os.path.getmtime(s) for s in srcs):
+            return LIB                                         # built by another process meanwhile
+        with open(os.path.join(CSRC, "lbm_kernels.cuh")) as fh:
+            text = "".join(line for line in fh if "griddepcontrol" not in line)
+        scratch = os.path.join(OUT, "lbm_kernels_nopdl.cuh")
+        with open(scratch + ".tmp", "w") as fh:
+            fh.write(text)
+        os.replace(scratch + ".tmp", scratch)
+        tmp = LIB + ".%d.tmp" % os.getpid()
+        subprocess.check_call([GXX, "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                               "-I", os.path.join(HERE, "stub"), "-I", OUT, "-I", CSRC, os.path.join(HERE, "emu.cpp"), "-o", tmp])
+        os.replace(tmp, LIB)
     return LIB
 
 

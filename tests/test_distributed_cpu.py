@@ -265,6 +265,7 @@ def test_product_kernel_and_exchanger_in_strips_gloo(world, nx, ny):
     """Strips of the product's own kernel source + the product's halo exchanger equal the single-domain run of the same
     kernel BIT FOR BIT (and the oracle to 1e-12): the N > 1 data path, minus the GPU, on world_size 2 and 3."""
     steps = 15
+    lib, dp = _load_emu()                 # built once here, before the ranks start
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -275,7 +276,6 @@ def test_product_kernel_and_exchanger_in_strips_gloo(world, nx, ny):
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
-    lib, dp = _load_emu()
     p = O.Params(nx, ny, Re=400, collision="MRT")
     rates = np.array([p.uLB, p.omega, p.omegam, p.omega_e, p.omega_eps, p.omega_q, 1.0 / p.omega])
     f1 = np.empty((9, nx, ny)); rho1 = np.empty((nx, ny)); u1 = np.empty((2, nx, ny))
